@@ -1,0 +1,136 @@
+/*
+ * pax.h -- C ABI of libpax.so: the B200 (sm_100a) sCBCT physics path.
+ *
+ * Drop-in boundary for the one hot path of nadeemlab/Physics-ArX: cone-beam
+ * forward projection (Ax), scatter/noise injection, FDK-weighted backprojection
+ * (Atb) and the OS-SART update with its W / V weights.  The reference reaches
+ * this arithmetic through five TIGRE calls in
+ *   Physics-based-Augmentation/OSSART-Reconstruction/pCT_CBCT_Reconstruction.py
+ * (:67 geometry_default, :86 Ax, :88 CTnoise.add, :103 ossart).  TIGRE's own
+ * native boundary (Cython _Ax_ext/_Atb_ext -> interpolation_projection(),
+ * voxel_backprojection(); SURVEY.md 8(b), recalled -- TIGRE is not vendored) is
+ * host-pointer in / host-pointer out and blocking.  This boundary differs on
+ * purpose: DEVICE pointers owned by the caller, asynchronous on the caller's
+ * stream, nothing allocated per call, so that a whole OS-SART run stays resident
+ * in HBM.  The ctypes binding a maintainer would add is in INTEGRATION.md.
+ *
+ * Conventions: volumes (Z,Y,X) C-order float32, projections (N,V,U) C-order
+ * float32, mm and radians.  Every function returns
+ * PAX_OK (0) or a negative PaxStatus; the message for the calling thread's last
+ * failure is pax_last_error().  No C++ exception crosses this boundary.
+ */
+#ifndef PAX_H_
+#define PAX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAX_VERSION 100
+
+typedef enum PaxStatus {
+    PAX_OK = 0,
+    PAX_ERR_INVALID = -1,   /* bad argument (NULL, range, unsupported geometry) */
+    PAX_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed */
+    PAX_ERR_NOMEM = -3
+} PaxStatus;
+
+/* geo.nVoxel / dVoxel / nDetector / dDetector / accuracy of the reference's
+ * geometry bag (pCT_CBCT_Reconstruction.py:67-83).  sVoxel = nVoxel*dVoxel. */
+typedef struct PaxGeo {
+    int32_t nVoxelZ, nVoxelY, nVoxelX;
+    int32_t nDetecV, nDetecU;
+    double dVoxelZ, dVoxelY, dVoxelX;   /* mm */
+    double dDetecV, dDetecU;            /* mm */
+    double accuracy;                    /* ray step in voxel units (TIGRE default 0.5) */
+} PaxGeo;
+
+/* One row per projection angle, the per-angle broadcast TIGRE's check_geo makes. */
+#define PAX_ANGLE_STRIDE 8
+/* [theta, DSD, DSO, offOrigZ, offOrigY, offOrigX, offDetV, offDetU] (doubles) */
+
+typedef struct PaxPlan PaxPlan;   /* per-geometry device constants; opaque */
+
+/* Epilogue of the forward projector.  P0/P1 = line integrals of volume channel 0/1,
+ * L = chord length (mm) of the ray through the W box.
+ *   PAX_AX_PLAIN    out = a0*P0 + a1*P1 + c*L      (a1 ignored without channel 1)
+ *   PAX_AX_RESIDUAL out = W * (b - P0), W = 1/L (0 where L <= w_thr)   [OS-SART, A.6]
+ * The scatter transfer of the reference (AddImages.cxx:57-62 adds the artifact
+ * volume to the planning CT before projecting) is PLAIN with a0 = 1, a1 = scale. */
+#define PAX_AX_PLAIN 0
+#define PAX_AX_RESIDUAL 1
+typedef struct PaxAxEpilogue {
+    int32_t mode;
+    float a0, a1, c;
+    const float *b;                 /* device, (count,V,U): measured projections of these angles */
+    float w_half_z, w_half_y, w_half_x;   /* W box half sizes, mm (geo.w_box) */
+    float w_thr;                    /* chord lengths <= w_thr give W = 0 */
+    double *sumsq;                  /* optional device scalar: += sum (b-P0)^2 (computel2) */
+    unsigned long long *nsamples;   /* optional device scalar: += trilinear samples taken */
+} PaxAxEpilogue;
+
+/* What the backprojector does with the accumulated sum  acc = sum_angles w * bilinear(proj):
+ *   PAX_ATB_STORE   vol  = acc
+ *   PAX_ATB_ADD     vol += acc
+ *   PAX_ATB_SART    vol  = max(0?, vol + lambda * inv_v[y,x] * acc)     [A.6 update + clip] */
+#define PAX_ATB_STORE 0
+#define PAX_ATB_ADD 1
+#define PAX_ATB_SART 2
+typedef struct PaxAtbEpilogue {
+    int32_t mode;
+    int32_t noneg;
+    float lambda;
+    const float *inv_v;             /* device (Y,X): 1/V_s, 0 where V_s == 0 */
+} PaxAtbEpilogue;
+
+int pax_version(void);
+const char *pax_last_error(void);
+
+/* replaces tigre's per-call geometry marshalling (Ax.py/Atb.py -> _Ax_ext/_Atb_ext) */
+int pax_plan_create(const PaxGeo *geo, const double *angle_rows, int n_angles, PaxPlan **out);
+int pax_plan_destroy(PaxPlan *plan);
+int pax_plan_n_angles(const PaxPlan *plan);
+
+/* Resident volume layout ("z-column": (Y+2, X+2, Zp) floats, z fastest, zero rim).
+ * pax_vol_elems = floats per channel.  pack/unpack convert from/to (Z,Y,X). */
+size_t pax_vol_elems(const PaxPlan *plan);
+int pax_vol_pack(const PaxPlan *plan, const float *vol_zyx, float *vol_res, void *stream);
+int pax_vol_unpack(const PaxPlan *plan, const float *vol_res, float *vol_zyx, void *stream);
+
+/* tigre.Ax(img, geo, angles, 'interpolated')  -- reference :86; angles [first, first+count)
+ * of the plan; vol_res1 may be NULL (single channel). proj_out is (count,V,U). */
+int pax_ax(const PaxPlan *plan, const float *vol_res0, const float *vol_res1, int first, int count,
+           float *proj_out, const PaxAxEpilogue *epi, void *stream);
+
+/* tigre.Atb(proj, geo, angles, 'FDK')  -- reached via ossart, reference :103.
+ * proj is (count,V,U) for angles [first, first+count); vol_res is in resident layout. */
+int pax_atb(const PaxPlan *plan, const float *proj, int first, int count, float *vol_res,
+            const PaxAtbEpilogue *epi, void *stream);
+
+/* x = max(0?, x + lambda*inv_v*upd): the update when upd was summed across GPUs first */
+int pax_sart_update(const PaxPlan *plan, float *x_res, const float *upd_res, const float *inv_v,
+                    float lambda, int noneg, void *stream);
+
+/* IterativeReconAlg.set_w / set_v (A.5).  w_out (count,V,U); v_out (Y,X) = mean_z Atb_FDK(ones)
+ * on the geometry with dVoxel scaled by vscale. */
+int pax_compute_w(const PaxPlan *plan, int first, int count, float half_z, float half_y,
+                  float half_x, float thr, float *w_out, void *stream);
+int pax_compute_v(const PaxPlan *plan, int first, int count, double vscale, float *v_out,
+                  void *stream);
+
+/* max over n floats -> *out_dev (device float) */
+int pax_reduce_max(const float *x, size_t n, float *out_dev, void *stream);
+
+/* tigre.utilities.CTnoise.add -- reference :88.  In place on n floats whose global
+ * element index starts at index0 (noise is a function of (seed, global index) only, so
+ * it does not depend on how projections are sharded).  *max_dev = max(proj). */
+int pax_ctnoise(float *proj, size_t n, uint64_t index0, double I0, double mean, double std,
+                const float *max_dev, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAX_H_ */

@@ -1,0 +1,95 @@
+"""ctypes binding of libpax.so (include/pax.h).  No CPU fallback: a missing library is fatal."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpax.so")
+
+PAX_AX_PLAIN, PAX_AX_RESIDUAL = 0, 1
+PAX_ATB_STORE, PAX_ATB_ADD, PAX_ATB_SART = 0, 1, 2
+ANGLE_STRIDE = 8
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class PaxGeo(ctypes.Structure):
+    _fields_ = [("nVoxelZ", ctypes.c_int32), ("nVoxelY", ctypes.c_int32), ("nVoxelX", ctypes.c_int32),
+                ("nDetecV", ctypes.c_int32), ("nDetecU", ctypes.c_int32),
+                ("dVoxelZ", ctypes.c_double), ("dVoxelY", ctypes.c_double), ("dVoxelX", ctypes.c_double),
+                ("dDetecV", ctypes.c_double), ("dDetecU", ctypes.c_double),
+                ("accuracy", ctypes.c_double)]
+
+
+class PaxAxEpilogue(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("a0", ctypes.c_float), ("a1", ctypes.c_float),
+                ("c", ctypes.c_float), ("b", ctypes.c_void_p),
+                ("w_half_z", ctypes.c_float), ("w_half_y", ctypes.c_float), ("w_half_x", ctypes.c_float),
+                ("w_thr", ctypes.c_float), ("sumsq", ctypes.c_void_p), ("nsamples", ctypes.c_void_p)]
+
+
+class PaxAtbEpilogue(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("noneg", ctypes.c_int32), ("lambda_", ctypes.c_float),
+                ("inv_v", ctypes.c_void_p)]
+
+
+# every symbol include/pax.h declares: (name, restype, argtypes)
+_VP = ctypes.c_void_p
+SYMBOLS = [
+    ("pax_version", ctypes.c_int, []),
+    ("pax_last_error", ctypes.c_char_p, []),
+    ("pax_plan_create", ctypes.c_int, [ctypes.POINTER(PaxGeo), c_double_p, ctypes.c_int,
+                                       ctypes.POINTER(_VP)]),
+    ("pax_plan_destroy", ctypes.c_int, [_VP]),
+    ("pax_plan_n_angles", ctypes.c_int, [_VP]),
+    ("pax_vol_elems", ctypes.c_size_t, [_VP]),
+    ("pax_vol_pack", ctypes.c_int, [_VP, _VP, _VP, _VP]),
+    ("pax_vol_unpack", ctypes.c_int, [_VP, _VP, _VP, _VP]),
+    ("pax_ax", ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
+                              ctypes.POINTER(PaxAxEpilogue), _VP]),
+    ("pax_atb", ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
+                               ctypes.POINTER(PaxAtbEpilogue), _VP]),
+    ("pax_sart_update", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_float, ctypes.c_int, _VP]),
+    ("pax_compute_w", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                     ctypes.c_float, ctypes.c_float, _VP, _VP]),
+    ("pax_compute_v", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_double, _VP, _VP]),
+    ("pax_reduce_max", ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP]),
+    ("pax_ctnoise", ctypes.c_int, [_VP, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_double,
+                                   ctypes.c_double, ctypes.c_double, _VP, ctypes.c_uint64, _VP]),
+]
+
+_lib = None
+
+
+class PaxError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """dlopen csrc/libpax.so and bind every declared symbol; raise loudly if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PaxError(
+            f"{LIB_PATH} is missing: build it with `python -m physics_arx_b200.csrc.build` "
+            "(nvcc, sm_100a).  This package has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)   # AttributeError if the .so does not export it
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.pax_version() != 100:
+        raise PaxError(f"libpax.so version {lib.pax_version()} does not match this package (100)")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().pax_last_error().decode(errors="replace")
+        if status == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise PaxError(f"{what}: {msg} (status {status})")

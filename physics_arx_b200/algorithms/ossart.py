@@ -1,0 +1,187 @@
+"""Device-resident OS-SART (``tigre.algorithms.ossart``; reference call site
+pCT_CBCT_Reconstruction.py:101-103, algorithm SURVEY.md A.6).
+
+    x <- max(0, x + lambda * V_s^-1 * Atb_FDK(W_s * (b_s - Ax(x))))    per subset s
+    lambda <- lambda * lmbda_red                                        per iteration
+
+TIGRE runs each Ax/Atb host-array in / host-array out and does the residual, weight
+and update arithmetic in NumPy between PCIe round trips.  Here the
+iterate, the projections and the V maps stay in HBM for the whole run: one kernel
+forms W*(b - Ax(x)) (W analytic, never materialised), one kernel backprojects and
+applies the update.  With a ``torch.distributed`` group the angles of every subset are
+interleaved over the ranks, each rank backprojects its residuals into a partial update,
+the partials are summed with one NCCL all-reduce per subset and every rank applies the
+(non-linear) clip after the sum.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..geometry import order_subsets
+from ..projector import Plan, _device_from_gpuids, _to_cuda
+from ..dist import shard_blocks, subset_geometry
+
+
+def _dist_info(group, distributed):
+    import torch.distributed as dist
+    if distributed is False or not (dist.is_available() and dist.is_initialized()):
+        return None, 0, 1
+    if distributed is None and group is None:
+        return None, 0, 1
+    g = group if group is not None else dist.group.WORLD
+    return g, dist.get_rank(g), dist.get_world_size(g)
+
+
+class OSSARTState:
+    """Set-up products of one OS-SART problem (the role of TIGRE's IterativeReconAlg)."""
+
+    def __init__(self, proj, geo, angles, blocksize=20, OrderStrategy=None, w_variant="matlab",
+                 v_variant="A", group=None, distributed=None, device=None, seed=0):
+        import torch.distributed as dist
+        angles = np.asarray(angles, dtype=np.float64)
+        if angles.ndim == 2:
+            geo.check_geo(angles)
+            angles = angles[:, 0]
+        n = angles.shape[0]
+        self.group, self.rank, self.world = _dist_info(group, distributed)
+        self.geo, self.n = geo, n
+        self.w_variant = w_variant
+        self.blocks = order_subsets(n, blocksize, OrderStrategy, seed)
+        local, self.ranges = shard_blocks(self.blocks, self.rank, self.world)
+        self.local_idx = local
+        dev = proj.device
+        # a rank may own no angle at all (n < world): keep one dummy angle so a plan exists
+        plan_idx = local if len(local) else np.array([0])
+        self.plan = Plan(subset_geometry(geo, plan_idx, n), angles[plan_idx], device=dev.index)
+        if len(local) == n and np.array_equal(local, np.arange(n)):
+            self.b = proj                                   # ordered, single rank: no copy
+        else:
+            self.b = proj[torch.as_tensor(local, device=dev, dtype=torch.long)].contiguous()
+        # V_s (A.5): a sum over the subset's angles, so partial sums all-reduce exactly
+        p = self.plan
+        V = torch.zeros((len(self.blocks), p.ny, p.nx), dtype=torch.float32, device=dev)
+        if v_variant == "A":
+            for s, (first, count) in enumerate(self.ranges):
+                if count:
+                    p.compute_v(first, count, out=V[s])
+        elif v_variant == "B":
+            V.copy_(torch.from_numpy(_v_variant_b(geo, angles, self.blocks)).to(dev))
+            if self.world > 1:
+                V /= self.world
+        else:
+            raise ValueError(f"unknown V variant {v_variant!r}")
+        if self.world > 1:
+            dist.all_reduce(V, group=self.group)
+        self.inv_v = torch.where(V > 1e-12, 1.0 / V, torch.zeros_like(V)).contiguous()
+        self.max_count = max((c for _, c in self.ranges), default=0)
+        self.resid = torch.empty((max(self.max_count, 1), p.nv, p.nu), dtype=torch.float32, device=dev)
+        self.upd = p.new_volume() if self.world > 1 else None
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def subset_step(self, x_res, s, lam, noneg=True, computel2=False):
+        import torch.distributed as dist
+        p = self.plan
+        first, count = self.ranges[s]
+        ss = self.sumsq if computel2 else None
+        if self.world == 1:
+            p.ax_residual(x_res, self.b[first:first + count], first, count, self.resid,
+                          self.w_variant, ss)
+            p.atb(self.resid, first, count, x_res, _lib.PAX_ATB_SART, self.inv_v[s], lam, noneg)
+            return
+        if count:
+            p.ax_residual(x_res, self.b[first:first + count], first, count, self.resid,
+                          self.w_variant, ss)
+            p.atb(self.resid, first, count, self.upd, _lib.PAX_ATB_STORE)
+        else:
+            self.upd.zero_()
+        dist.all_reduce(self.upd, group=self.group)
+        p.sart_update(x_res, self.upd, self.inv_v[s], lam, noneg)
+
+    def iteration(self, x_res, lam, noneg=True, computel2=False):
+        for s in range(len(self.blocks)):
+            self.subset_step(x_res, s, lam, noneg, computel2)
+
+
+def _v_variant_b(geo, angles, blocks):
+    """2021-Python analytic V (SURVEY.md A.5 variant B); host NumPy, tiny."""
+    g, rows = geo.pack(angles)
+    ny, nx = int(g[1]), int(g[2])
+    dv = np.asarray(geo.dVoxel, float)
+    sv = np.asarray(geo.sVoxel, float)
+    x = -sv[2] / 2 + dv[2] / 2 + dv[2] * np.arange(nx) + rows[0, 5]
+    y = -sv[1] / 2 + dv[1] / 2 + dv[1] * np.arange(ny) + rows[0, 4]
+    yy, xx = np.meshgrid(y, x, indexing="ij")
+    out = np.zeros((len(blocks), ny, nx), dtype=np.float32)
+    for s, idx in enumerate(blocks):
+        acc = np.zeros((ny, nx))
+        for i in idx:
+            A = rows[i, 0] + np.pi / 2
+            acc += (rows[i, 2] / (rows[i, 2] + yy * np.sin(-A) - xx * np.cos(-A))) ** 2
+        out[s] = acc
+    return out
+
+
+def ossart(proj, geo, angles, niter, **kwargs):
+    """OS-SART with TIGRE's signature and defaults (A.6).
+
+    kwargs: blocksize=20, lmbda=1, lmbda_red=0.99, OrderStrategy=None, init=None,
+    noneg=True, verbose=False, computel2=False, gpuids=None; build extras: w_variant,
+    v_variant, group / distributed (angle sharding over a torch.distributed group).
+    Returns the (Z,Y,X) float32 volume (NumPy in -> NumPy out); with computel2 also the
+    per-iteration ||b - Ax||_2.
+    """
+    blocksize = kwargs.pop("blocksize", 20)
+    lmbda = float(kwargs.pop("lmbda", 1.0))
+    lmbda_red = float(kwargs.pop("lmbda_red", 0.99))
+    order = kwargs.pop("OrderStrategy", None)
+    init = kwargs.pop("init", None)
+    noneg = kwargs.pop("noneg", True)
+    verbose = kwargs.pop("verbose", False)
+    computel2 = kwargs.pop("computel2", False)
+    gpuids = kwargs.pop("gpuids", None)
+    if kwargs.pop("Quameasopts", None) is not None:
+        raise NotImplementedError("Quameasopts is not on this path (commented out in the reference, :103)")
+    state_kw = {k: kwargs.pop(k) for k in ("w_variant", "v_variant", "group", "distributed") if k in kwargs}
+    if kwargs:
+        raise TypeError(f"ossart: unexpected keyword arguments {sorted(kwargs)}")
+    if not torch.cuda.is_available():
+        raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", _device_from_gpuids(gpuids))
+    b, was_np = _to_cuda(proj, dev, "proj")
+    nang = np.asarray(angles).shape[0]
+    nv, nu = (int(v) for v in geo.nDetector)
+    if tuple(b.shape) != (nang, nv, nu):
+        raise ValueError(f"proj shape {tuple(b.shape)} != (N, *geo.nDetector) {(nang, nv, nu)}")
+    st = OSSARTState(b, geo, angles, blocksize, order, **state_kw)
+    p = st.plan
+    if init is None:
+        x = p.new_volume()
+    elif isinstance(init, str):
+        raise NotImplementedError(f"init={init!r} is not on this path (reference uses the default, zeros)")
+    else:
+        x0, _ = _to_cuda(init, b.device, "init")
+        x = p.pack(x0)
+    lam = lmbda
+    l2 = []
+    for it in range(int(niter)):
+        if computel2:
+            st.sumsq.zero_()
+        st.iteration(x, lam, noneg, computel2)
+        if computel2:
+            ss = st.sumsq.clone()
+            if st.world > 1:
+                dist.all_reduce(ss, group=st.group)
+            l2.append(float(ss.sqrt().item()))
+        if verbose and st.rank == 0:
+            print(f"OS-SART iteration {it + 1}/{niter}, lambda={lam:.4f}")
+        lam *= lmbda_red
+    out = p.unpack(x)
+    out = out.cpu().numpy() if was_np else out
+    return (out, np.array(l2)) if computel2 else out
+
+
+OS_SART = ossart

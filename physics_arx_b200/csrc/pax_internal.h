@@ -1,0 +1,85 @@
+// Internal declarations shared by the libpax translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "pax.h"
+
+#define PAX_ZOFF 4   // z index of voxel 0 inside a resident column (keeps float4 alignment)
+
+// Per-angle constants, computed in double on the host (plan.cu).
+struct AngleDev {
+    // ray frame in the padded index space of the resident volume: voxel (k,j,i) centre
+    // sits at (x,y,z) = (i+1, j+1, k+PAX_ZOFF).   [SURVEY.md A.2/A.3]
+    double sx, sy, sz;     // source
+    double ox, oy, oz;     // centre of pixel (v=0,u=0)
+    double ux, uy;         // step per +1 in u (no z component: u-hat is in-plane)
+    double vz;             // step per +1 in v (v-hat = z)
+    // the same frame in mm relative to the centre of the W box (= offOrigin)   [A.5]
+    float wsx, wsy, wsz;
+    float wox, woy, woz;
+    float wux, wuy, wvz;
+    // voxel-driven backprojection   [A.4]
+    float cosv, sinv, DSD, DSO;
+    float offOZ, offOY, offOX, offDV, offDU;
+    float pad_;
+};
+
+struct PaxPlan {
+    PaxGeo geo;
+    int n_angles;
+    int device;
+    int nyp, nxp, nzp;          // resident (padded) dims
+    size_t vol_elems;
+    AngleDev *d_angles;
+    std::vector<AngleDev> h_angles;
+};
+
+int pax_set_error(int code, const char *fmt, ...);
+
+#define PAX_CHECK_CUDA(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return pax_set_error(PAX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,            \
+                                 cudaGetErrorString(e__), __FILE__, __LINE__);            \
+    } while (0)
+
+#define PAX_REQUIRE(cond, ...)                                                            \
+    do {                                                                                  \
+        if (!(cond)) return pax_set_error(PAX_ERR_INVALID, __VA_ARGS__);                  \
+    } while (0)
+
+static inline int pax_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+// chord length (mm) of the segment source->pixel through the box |x|<=hx, |y|<=hy, |z|<=hz
+__device__ __forceinline__ float box_chord(float sx, float sy, float sz, float dx, float dy, float dz,
+                                           float hx, float hy, float hz)
+{
+    float t0 = 0.f, t1 = 1.f;
+    bool miss = false;
+    {
+        if (dx == 0.f) miss |= (sx < -hx || sx > hx);
+        else { const float r = 1.f / dx; const float a = (-hx - sx) * r, b = (hx - sx) * r;
+               t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+        if (dy == 0.f) miss |= (sy < -hy || sy > hy);
+        else { const float r = 1.f / dy; const float a = (-hy - sy) * r, b = (hy - sy) * r;
+               t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+        if (dz == 0.f) miss |= (sz < -hz || sz > hz);
+        else { const float r = 1.f / dz; const float a = (-hz - sz) * r, b = (hz - sz) * r;
+               t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+    }
+    if (miss || !(t1 > t0)) return 0.f;
+    return (t1 - t0) * sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+__device__ __forceinline__ float pax_ray_chord(const AngleDev &A, int u, int v, float hx, float hy, float hz)
+{
+    const float px = A.wox + u * A.wux, py = A.woy + u * A.wuy, pz = A.woz + v * A.wvz;
+    return box_chord(A.wsx, A.wsy, A.wsz, px - A.wsx, py - A.wsy, pz - A.wsz, hx, hy, hz);
+}
+#endif  // __CUDACC__

@@ -1,0 +1,344 @@
+// Plan (per-geometry device constants), error reporting, layout conversion, and the
+// small elementwise / reduction kernels of the path.  sm_100a only.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "pax_internal.h"
+
+// ----------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+int pax_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *pax_last_error(void) { return g_err; }
+extern "C" int pax_version(void) { return PAX_VERSION; }
+
+// ------------------------------------------------------------------------------- plan
+extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, PaxPlan **out)
+{
+    PAX_REQUIRE(geo && rows && out, "pax_plan_create: NULL argument");
+    PAX_REQUIRE(n >= 1, "pax_plan_create: n_angles=%d", n);
+    PAX_REQUIRE(geo->nVoxelX >= 1 && geo->nVoxelY >= 1 && geo->nVoxelZ >= 1 &&
+                    geo->nDetecU >= 1 && geo->nDetecV >= 1,
+                "pax_plan_create: non-positive dimensions");
+    PAX_REQUIRE(geo->dVoxelX > 0 && geo->dVoxelY > 0 && geo->dVoxelZ > 0 && geo->dDetecU > 0 &&
+                    geo->dDetecV > 0 && geo->accuracy > 0,
+                "pax_plan_create: non-positive spacing/accuracy");
+    PAX_REQUIRE((long)geo->nVoxelX < 8192 && (long)geo->nVoxelY < 8192 && (long)geo->nVoxelZ < 8192,
+                "pax_plan_create: volume dimension too large");
+    PaxPlan *p = new (std::nothrow) PaxPlan();
+    if (!p) return pax_set_error(PAX_ERR_NOMEM, "pax_plan_create: out of host memory");
+    p->geo = *geo;
+    p->n_angles = n;
+    p->nyp = geo->nVoxelY + 2;
+    p->nxp = geo->nVoxelX + 2;
+    p->nzp = ((geo->nVoxelZ + PAX_ZOFF + 1) + 3) / 4 * 4;
+    p->vol_elems = (size_t)p->nyp * p->nxp * p->nzp;
+    if (p->vol_elems >= (size_t)1 << 31) {
+        delete p;
+        return pax_set_error(PAX_ERR_INVALID, "pax_plan_create: resident volume exceeds 2^31 elements");
+    }
+    p->h_angles.resize(n);
+    const double nX = geo->nVoxelX, nY = geo->nVoxelY, nZ = geo->nVoxelZ;
+    const double dX = geo->dVoxelX, dY = geo->dVoxelY, dZ = geo->dVoxelZ;
+    for (int i = 0; i < n; ++i) {
+        const double *a = rows + (size_t)i * PAX_ANGLE_STRIDE;
+        const double th = a[0], DSD = a[1], DSO = a[2];
+        const double oz = a[3], oy = a[4], ox = a[5], ov = a[6], ou = a[7];
+        if (!(DSO > 0 && DSD > DSO)) {
+            delete p;
+            return pax_set_error(PAX_ERR_INVALID, "pax_plan_create: need DSD > DSO > 0 (angle %d)", i);
+        }
+        const double c = cos(th), s = sin(th);
+        AngleDev &A = p->h_angles[i];
+        // world -> index: (r - off + sVoxel/2 - dVoxel/2)/dVoxel, then the padding shift
+        const double bx = -ox + 0.5 * nX * dX - 0.5 * dX;
+        const double by = -oy + 0.5 * nY * dY - 0.5 * dY;
+        const double bz = -oz + 0.5 * nZ * dZ - 0.5 * dZ;
+        const double u0 = (0.5 - 0.5 * geo->nDetecU) * geo->dDetecU + ou;
+        const double v0 = (0.5 - 0.5 * geo->nDetecV) * geo->dDetecV + ov;
+        const double Sx = DSO * c, Sy = DSO * s, Sz = 0.0;
+        const double Px = -(DSD - DSO) * c - u0 * s, Py = -(DSD - DSO) * s + u0 * c, Pz = v0;
+        A.sx = (Sx + bx) / dX + 1.0;
+        A.sy = (Sy + by) / dY + 1.0;
+        A.sz = (Sz + bz) / dZ + PAX_ZOFF;
+        A.ox = (Px + bx) / dX + 1.0;
+        A.oy = (Py + by) / dY + 1.0;
+        A.oz = (Pz + bz) / dZ + PAX_ZOFF;
+        A.ux = -s * geo->dDetecU / dX;
+        A.uy = c * geo->dDetecU / dY;
+        A.vz = geo->dDetecV / dZ;
+        A.wsx = (float)(Sx - ox); A.wsy = (float)(Sy - oy); A.wsz = (float)(Sz - oz);
+        A.wox = (float)(Px - ox); A.woy = (float)(Py - oy); A.woz = (float)(Pz - oz);
+        A.wux = (float)(-s * geo->dDetecU); A.wuy = (float)(c * geo->dDetecU);
+        A.wvz = (float)geo->dDetecV;
+        A.cosv = (float)c; A.sinv = (float)s; A.DSD = (float)DSD; A.DSO = (float)DSO;
+        A.offOZ = (float)oz; A.offOY = (float)oy; A.offOX = (float)ox;
+        A.offDV = (float)ov; A.offDU = (float)ou;
+        A.pad_ = 0.f;
+    }
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_angles, sizeof(AngleDev) * n);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(p->d_angles, p->h_angles.data(), sizeof(AngleDev) * n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (p->d_angles) cudaFree(p->d_angles);
+        delete p;
+        return pax_set_error(PAX_ERR_CUDA, "pax_plan_create: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return PAX_OK;
+}
+
+extern "C" int pax_plan_destroy(PaxPlan *p)
+{
+    if (!p) return PAX_OK;
+    if (p->d_angles) cudaFree(p->d_angles);
+    delete p;
+    return PAX_OK;
+}
+
+extern "C" int pax_plan_n_angles(const PaxPlan *p) { return p ? p->n_angles : 0; }
+extern "C" size_t pax_vol_elems(const PaxPlan *p) { return p ? p->vol_elems : 0; }
+
+// ------------------------------------------------------------------ layout conversion
+// (Z,Y,X) x-fastest  <->  resident (Y+2, X+2, Zp) z-fastest: a 32x32 smem transpose per y.
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_transpose(const float *__restrict__ src,
+                                                   float *__restrict__ dst, int nz, int ny, int nx,
+                                                   int nxp, int nzp)
+{
+    __shared__ float tile[32][33];
+    const int y = blockIdx.z;
+    const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    if (PACK) {
+        for (int r = ty; r < 32; r += 8) {
+            const int z = z0 + r, x = x0 + tx;
+            tile[r][tx] = (z < nz && x < nx) ? src[((size_t)z * ny + y) * nx + x] : 0.f;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int x = x0 + r, z = z0 + tx;
+            if (x < nx && z < nz)
+                dst[((size_t)(y + 1) * nxp + (x + 1)) * nzp + PAX_ZOFF + z] = tile[tx][r];
+        }
+    } else {
+        for (int r = ty; r < 32; r += 8) {
+            const int x = x0 + r, z = z0 + tx;
+            tile[r][tx] = (x < nx && z < nz)
+                              ? src[((size_t)(y + 1) * nxp + (x + 1)) * nzp + PAX_ZOFF + z] : 0.f;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int z = z0 + r, x = x0 + tx;
+            if (z < nz && x < nx) dst[((size_t)z * ny + y) * nx + x] = tile[tx][r];
+        }
+    }
+}
+
+extern "C" int pax_vol_pack(const PaxPlan *p, const float *vol_zyx, float *vol_res, void *stream)
+{
+    PAX_REQUIRE(p && vol_zyx && vol_res, "pax_vol_pack: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PAX_CHECK_CUDA(cudaMemsetAsync(vol_res, 0, p->vol_elems * sizeof(float), st));
+    dim3 grid(pax_cdiv(p->geo.nVoxelX, 32), pax_cdiv(p->geo.nVoxelZ, 32), p->geo.nVoxelY);
+    k_transpose<true><<<grid, 256, 0, st>>>(vol_zyx, vol_res, p->geo.nVoxelZ, p->geo.nVoxelY,
+                                            p->geo.nVoxelX, p->nxp, p->nzp);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
+extern "C" int pax_vol_unpack(const PaxPlan *p, const float *vol_res, float *vol_zyx, void *stream)
+{
+    PAX_REQUIRE(p && vol_zyx && vol_res, "pax_vol_unpack: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(pax_cdiv(p->geo.nVoxelX, 32), pax_cdiv(p->geo.nVoxelZ, 32), p->geo.nVoxelY);
+    k_transpose<false><<<grid, 256, 0, st>>>(vol_res, vol_zyx, p->geo.nVoxelZ, p->geo.nVoxelY,
+                                             p->geo.nVoxelX, p->nxp, p->nzp);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
+// ------------------------------------------------------------------------- SART update
+// x = max(0, x + lambda*inv_v[y,x]*upd) over the interior of the resident layout.
+__global__ void __launch_bounds__(256) k_sart_update(float *__restrict__ x,
+                                                     const float *__restrict__ upd,
+                                                     const float *__restrict__ inv_v, int nz, int ny,
+                                                     int nx, int nxp, int nzp, float lambda, int noneg)
+{
+    // one thread per (column, 4 z): consecutive threads walk z fastest -> coalesced float4
+    const int nz4 = (nz + 3) / 4;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long ncol = (long)ny * nx;
+    if (t >= ncol * nz4) return;
+    const int q = (int)(t % nz4);
+    const long col = t / nz4;
+    const int yy = (int)(col / nx), xx = (int)(col % nx);
+    const float s = lambda * inv_v[col];
+    const size_t base = ((size_t)(yy + 1) * nxp + (xx + 1)) * nzp + PAX_ZOFF + 4 * q;
+    float4 a = *reinterpret_cast<const float4 *>(x + base);
+    const float4 b = *reinterpret_cast<const float4 *>(upd + base);
+    a.x = fmaf(s, b.x, a.x); a.y = fmaf(s, b.y, a.y); a.z = fmaf(s, b.z, a.z); a.w = fmaf(s, b.w, a.w);
+    if (noneg) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    const int zr = nz - 4 * q;   // valid z in this quad; never touch the zero rim
+    if (zr >= 4) {
+        *reinterpret_cast<float4 *>(x + base) = a;
+    } else {
+        x[base] = a.x;
+        if (zr > 1) x[base + 1] = a.y;
+        if (zr > 2) x[base + 2] = a.z;
+    }
+}
+
+extern "C" int pax_sart_update(const PaxPlan *p, float *x_res, const float *upd_res,
+                               const float *inv_v, float lambda, int noneg, void *stream)
+{
+    PAX_REQUIRE(p && x_res && upd_res && inv_v, "pax_sart_update: NULL argument");
+    const long n = (long)p->geo.nVoxelY * p->geo.nVoxelX * ((p->geo.nVoxelZ + 3) / 4);
+    k_sart_update<<<pax_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        x_res, upd_res, inv_v, p->geo.nVoxelZ, p->geo.nVoxelY, p->geo.nVoxelX, p->nxp, p->nzp, lambda,
+        noneg);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
+// -------------------------------------------------------------------------------- max
+__device__ __forceinline__ unsigned enc_ordered(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void __launch_bounds__(256) k_max(const float *__restrict__ x, size_t n, unsigned *out)
+{
+    float m = -INFINITY;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = x4[i];
+        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        m = fmaxf(m, x[i]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < 8 ? sm[threadIdx.x] : -INFINITY;
+        for (int o = 4; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(out, enc_ordered(m));
+    }
+}
+__global__ void k_max_decode(unsigned *out) { *reinterpret_cast<float *>(out) = dec_ordered(*out); }
+
+extern "C" int pax_reduce_max(const float *x, size_t n, float *out_dev, void *stream)
+{
+    PAX_REQUIRE(x && out_dev && n > 0, "pax_reduce_max: bad argument");
+    PAX_REQUIRE(((uintptr_t)x & 15) == 0, "pax_reduce_max: input must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    PAX_CHECK_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(float), st));
+    const int blocks = (int)std::min<size_t>(148 * 8, (n / 4 + 255) / 256 + 1);
+    k_max<<<blocks, 256, 0, st>>>(x, n, reinterpret_cast<unsigned *>(out_dev));
+    k_max_decode<<<1, 1, 0, st>>>(reinterpret_cast<unsigned *>(out_dev));
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
+// ------------------------------------------------------------------------------ noise
+// Philox4x32-10 (Salmon et al. 2011), one block of 4 words per projection pixel keyed by
+// (seed, global pixel index); same word assignment as oracle_ctnoise.
+__device__ __forceinline__ void philox4x32_10(unsigned c[4], unsigned k0, unsigned k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// CTnoise.add (reference :88) in double: I0 = 1e8 counts do not fit fp32.
+__global__ void __launch_bounds__(256) k_ctnoise(float *__restrict__ p, size_t n, uint64_t index0,
+                                                 double I0, double mean, double sd,
+                                                 const float *__restrict__ max_dev, uint64_t seed)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double m = (double)*max_dev;
+    const uint64_t idx = index0 + e;
+    unsigned c[4] = {(unsigned)idx, (unsigned)(idx >> 32), 0u, 0u};
+    philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+    const double inv32 = 1.0 / 4294967296.0;
+    const double u1 = ((double)c[0] + 0.5) * inv32, u2 = ((double)c[1] + 0.5) * inv32;
+    const double u3 = ((double)c[2] + 0.5) * inv32, u4 = ((double)c[3] + 0.5) * inv32;
+    const double lam = I0 * exp(-(double)p[e] / m);
+    double k;
+    if (lam < 512.0) {   // exact sequential inversion
+        double pk = exp(-lam), F = pk;
+        k = 0.0;
+        while (u1 > F && k < 4096.0) { k += 1.0; pk *= lam / k; F += pk; }
+    } else {             // rounded normal approximation
+        const double zp = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        k = floor(lam + sqrt(lam) * zp + 0.5);
+        if (k < 0.0) k = 0.0;
+    }
+    const double zg = sqrt(-2.0 * log(u3)) * cospi(2.0 * u4);
+    double I = k + mean + sd * zg;
+    if (I <= 0.0) I = 1e-6;
+    p[e] = (float)(-log(I / I0) * m);
+}
+
+extern "C" int pax_ctnoise(float *proj, size_t n, uint64_t index0, double I0, double mean, double sd,
+                           const float *max_dev, uint64_t seed, void *stream)
+{
+    PAX_REQUIRE(proj && max_dev && n > 0, "pax_ctnoise: bad argument");
+    PAX_REQUIRE(I0 > 0 && sd >= 0, "pax_ctnoise: need I0 > 0 and std >= 0");
+    k_ctnoise<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(proj, n, index0, I0, mean,
+                                                                             sd, max_dev, seed);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
+// ---------------------------------------------------------------------------------- W
+__global__ void __launch_bounds__(256) k_compute_w(const AngleDev *__restrict__ angles, int first,
+                                                   int nv, int nu, float hz, float hy, float hx,
+                                                   float thr, float *__restrict__ w)
+{
+    const int u = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int v = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int ia = blockIdx.z;
+    if (u >= nu || v >= nv) return;
+    const AngleDev A = angles[first + ia];
+    const float L = pax_ray_chord(A, u, v, hx, hy, hz);
+    w[((size_t)ia * nv + v) * nu + u] = L > thr ? 1.f / L : 0.f;
+}
+
+extern "C" int pax_compute_w(const PaxPlan *p, int first, int count, float hz, float hy, float hx,
+                             float thr, float *w_out, void *stream)
+{
+    PAX_REQUIRE(p && w_out, "pax_compute_w: NULL argument");
+    PAX_REQUIRE(first >= 0 && count >= 1 && first + count <= p->n_angles,
+                "pax_compute_w: angle range [%d,%d) outside plan (%d)", first, first + count, p->n_angles);
+    dim3 grid(pax_cdiv(p->geo.nDetecU, 32), pax_cdiv(p->geo.nDetecV, 8), count);
+    k_compute_w<<<grid, 256, 0, (cudaStream_t)stream>>>(p->d_angles, first, p->geo.nDetecV,
+                                                        p->geo.nDetecU, hz, hy, hx, thr, w_out);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}

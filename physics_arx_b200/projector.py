@@ -1,0 +1,231 @@
+"""``Ax`` / ``Atb`` with the reference's call surface, and the resident-volume ``Plan``.
+
+The reference calls ``tigre.Ax(img, geo, angles, 'interpolated', gpuids=gpuids)``
+(pCT_CBCT_Reconstruction.py:86) and reaches ``tigre.Atb(..., 'FDK')`` through
+``algs.ossart`` (:103).  Same names, argument order and error behaviour here
+(SURVEY.md 8(b)): float32 only (``TypeError``), shapes must match ``geo``
+(``ValueError``); NumPy in -> NumPy out, torch CUDA tensor in -> torch CUDA tensor out
+(zero-copy).  PyTorch is used for device memory and streams only; all arithmetic is
+in libpax.so (csrc/), called through the C ABI of include/pax.h.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .geometry import Geometry
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _device_from_gpuids(gpuids):
+    if gpuids is None:
+        return torch.cuda.current_device()
+    devices = getattr(gpuids, "devices", gpuids)
+    if isinstance(devices, (list, tuple)):
+        if len(devices) == 0:
+            raise ValueError("gpuids is empty")
+        return int(devices[0])
+    return int(devices)
+
+
+class Plan:
+    """Per-(geometry, angle list) device constants plus helpers on the resident layout.
+
+    The resident layout of a volume is libpax's z-fastest zero-rimmed array
+    (include/pax.h: pax_vol_pack); OS-SART keeps its iterate in that layout for the
+    whole run so that Ax and Atb never convert.
+    """
+
+    def __init__(self, geo: Geometry, angles, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        g, rows = geo.pack(angles)
+        self.geo = geo
+        self.n_angles = rows.shape[0]
+        self.nz, self.ny, self.nx = int(g[0]), int(g[1]), int(g[2])
+        self.nv, self.nu = int(g[3]), int(g[4])
+        cg = _lib.PaxGeo(self.nz, self.ny, self.nx, self.nv, self.nu, g[5], g[6], g[7], g[8], g[9], g[10])
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_plan_create(ctypes.byref(cg), rows.ctypes.data_as(_lib.c_double_p),
+                                                self.n_angles, ctypes.byref(handle)), "pax_plan_create")
+        self._h = handle
+        self.vol_elems = int(self.lib.pax_vol_elems(self._h))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.pax_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ volumes
+    def new_volume(self):
+        return torch.zeros(self.vol_elems, dtype=torch.float32, device=self.device)
+
+    def _check_vol(self, vol):
+        if vol.dtype != torch.float32:
+            raise TypeError("volume must be float32")
+        if tuple(vol.shape) != (self.nz, self.ny, self.nx):
+            raise ValueError(f"volume shape {tuple(vol.shape)} != geo.nVoxel {(self.nz, self.ny, self.nx)}")
+
+    def pack(self, vol, out=None):
+        """(Z,Y,X) float32 CUDA tensor -> resident layout."""
+        self._check_vol(vol)
+        vol = vol.contiguous()
+        out = torch.empty(self.vol_elems, dtype=torch.float32, device=self.device) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_vol_pack(self._h, _ptr(vol), _ptr(out), _stream()), "pax_vol_pack")
+        return out
+
+    def unpack(self, res, out=None):
+        out = torch.empty((self.nz, self.ny, self.nx), dtype=torch.float32, device=self.device) \
+            if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_vol_unpack(self._h, _ptr(res), _ptr(out), _stream()), "pax_vol_unpack")
+        return out
+
+    # --------------------------------------------------------------- projectors
+    def _w_box(self, w_variant):
+        (hz, hy, hx), thr = self.geo.w_box(w_variant)
+        return float(hz), float(hy), float(hx), float(thr)
+
+    def ax(self, res0, first=0, count=None, out=None, res1=None, a0=1.0, a1=0.0, c=0.0,
+           w_variant="matlab", nsamples=None):
+        """out[(count,V,U)] = a0*Ax(res0) + a1*Ax(res1) + c*chord.  (PAX_AX_PLAIN)"""
+        count = self.n_angles - first if count is None else count
+        if out is None:
+            out = torch.empty((count, self.nv, self.nu), dtype=torch.float32, device=self.device)
+        hz, hy, hx, thr = self._w_box(w_variant)
+        epi = _lib.PaxAxEpilogue(_lib.PAX_AX_PLAIN, a0, a1, c, None, hz, hy, hx, thr, None,
+                                 nsamples.data_ptr() if nsamples is not None else None)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_ax(self._h, _ptr(res0), _ptr(res1), first, count, _ptr(out),
+                                       ctypes.byref(epi), _stream()), "pax_ax")
+        return out
+
+    def ax_residual(self, res, b, first, count, out, w_variant="matlab", sumsq=None):
+        """out = W * (b - Ax(res)) for angles [first, first+count).  (PAX_AX_RESIDUAL)"""
+        hz, hy, hx, thr = self._w_box(w_variant)
+        epi = _lib.PaxAxEpilogue(_lib.PAX_AX_RESIDUAL, 1.0, 0.0, 0.0, b.data_ptr(), hz, hy, hx, thr,
+                                 sumsq.data_ptr() if sumsq is not None else None, None)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_ax(self._h, _ptr(res), None, first, count, _ptr(out),
+                                       ctypes.byref(epi), _stream()), "pax_ax")
+        return out
+
+    def atb(self, proj, first, count, out_res, mode=_lib.PAX_ATB_STORE, inv_v=None, lam=1.0, noneg=True):
+        epi = _lib.PaxAtbEpilogue(mode, int(bool(noneg)), float(lam),
+                                  inv_v.data_ptr() if inv_v is not None else None)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_atb(self._h, _ptr(proj), first, count, _ptr(out_res),
+                                        ctypes.byref(epi), _stream()), "pax_atb")
+        return out_res
+
+    def sart_update(self, x_res, upd_res, inv_v, lam, noneg=True):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_sart_update(self._h, _ptr(x_res), _ptr(upd_res), _ptr(inv_v),
+                                                float(lam), int(bool(noneg)), _stream()), "pax_sart_update")
+        return x_res
+
+    def compute_w(self, first=0, count=None, w_variant="matlab", out=None):
+        count = self.n_angles - first if count is None else count
+        if out is None:
+            out = torch.empty((count, self.nv, self.nu), dtype=torch.float32, device=self.device)
+        hz, hy, hx, thr = self._w_box(w_variant)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_compute_w(self._h, first, count, hz, hy, hx, thr, _ptr(out), _stream()),
+                       "pax_compute_w")
+        return out
+
+    def compute_v(self, first, count, out=None):
+        if out is None:
+            out = torch.empty((self.ny, self.nx), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_compute_v(self._h, first, count, self.geo.v_scale(), _ptr(out),
+                                              _stream()), "pax_compute_v")
+        return out
+
+
+def reduce_max(x):
+    """max over a float32 CUDA tensor -> 1-element CUDA tensor (stays on the device)."""
+    lib = _lib.load()
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pax_reduce_max(_ptr(x), x.numel(), _ptr(out), _stream()), "pax_reduce_max")
+    return out
+
+
+# ---------------------------------------------------------------- reference call surface
+def _to_cuda(arr, device, what):
+    """NumPy / torch input -> (float32 contiguous CUDA tensor, was_numpy)."""
+    if isinstance(arr, np.ndarray):
+        if arr.dtype != np.float32:
+            raise TypeError(f"{what} must be float32, got {arr.dtype}")
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=False), True
+    if isinstance(arr, torch.Tensor):
+        if arr.dtype != torch.float32:
+            raise TypeError(f"{what} must be float32, got {arr.dtype}")
+        if not arr.is_cuda:
+            return arr.contiguous().to(device), False
+        return arr.contiguous(), False
+    raise TypeError(f"{what} must be a numpy array or torch tensor, got {type(arr)}")
+
+
+def Ax(img, geo, angles, projection_type="interpolated", **kwargs):
+    """Forward projection, ``tigre.Ax`` surface (reference call site :86).
+
+    Extra keyword ``scatter=(art, scale)`` projects a second volume in the same pass and
+    returns ``Ax(img) + scale*Ax(art)`` -- the reference's image-domain scatter transfer
+    (AddImages.cxx:57-62) moved into the projection epilogue by linearity.
+    """
+    if projection_type not in ("interpolated", None):
+        raise ValueError(f"projection_type {projection_type!r} is not on this path "
+                         "(only 'interpolated', the projector the reference calls)")
+    if not torch.cuda.is_available():
+        raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
+    dev = torch.device("cuda", _device_from_gpuids(kwargs.get("gpuids")))
+    vol, was_np = _to_cuda(img, dev, "img")
+    plan = kwargs.get("plan") or Plan(geo, angles, device=vol.device.index)
+    res0 = plan.pack(vol)
+    res1, a1 = None, 0.0
+    if kwargs.get("scatter") is not None:
+        art, a1 = kwargs["scatter"]
+        art_t, _ = _to_cuda(art, vol.device, "scatter volume")
+        res1 = plan.pack(art_t)
+    out = plan.ax(res0, res1=res1, a0=1.0, a1=float(a1))
+    return out.cpu().numpy() if was_np else out
+
+
+def Atb(projections, geo, angles, backprojection_type="FDK", **kwargs):
+    """Backprojection, ``tigre.Atb`` surface ('FDK' weights)."""
+    if backprojection_type not in ("FDK", None):
+        raise ValueError(f"backprojection_type {backprojection_type!r} is not on this path "
+                         "(only 'FDK', the weights ossart uses)")
+    if not torch.cuda.is_available():
+        raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
+    dev = torch.device("cuda", _device_from_gpuids(kwargs.get("gpuids")))
+    proj, was_np = _to_cuda(projections, dev, "projections")
+    plan = kwargs.get("plan") or Plan(geo, angles, device=proj.device.index)
+    if tuple(proj.shape) != (plan.n_angles, plan.nv, plan.nu):
+        raise ValueError(f"projections shape {tuple(proj.shape)} != (N, *geo.nDetector) "
+                         f"{(plan.n_angles, plan.nv, plan.nu)}")
+    res = plan.new_volume()
+    plan.atb(proj, 0, plan.n_angles, res, _lib.PAX_ATB_STORE)
+    out = plan.unpack(res)
+    return out.cpu().numpy() if was_np else out
