@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the sCBCT generation loop (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C1] [--impl ours|reference]
+
+A step = one whole sCBCT volume: two-channel forward projection of (planning CT, artifact
+volume) with the scatter combine in its epilogue, Poisson + electronic noise, and OS-SART
+(20 iterations x 33 subsets at C2) -- synthetic seeded phantom, fp32.  `value` times the
+steps with inputs resident in HBM; `e2e` times the public host-buffer call
+(SCBCTPipeline.run_host: pinned host volumes in, reconstructed volume back to the host).
+For N > 1 the angles of each OS-SART subset are interleaved over the ranks and the partial
+updates are summed with one NCCL all-reduce per subset (strong scaling: the workload is
+fixed).  `--impl reference` times the float64 CPU oracle (the reference has no CPU
+implementation of this path; see oracle/oracle.c) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sCBCT volumes/sec (proj+scatter+OS-SART)"
+UNIT = "volumes/s"
+SCATTER_SCALE = 1.0
+
+
+def get_config(name):
+    from physics_arx_b200 import phantom
+    cfg = {"C1": phantom.config_c1, "C2": phantom.config_c2}[name]()
+    return cfg
+
+
+def describe(cfg, n_gpus):
+    geo = cfg["geo"]
+    nsub = -(-len(cfg["angles"]) // cfg["blocksize"])
+    return {
+        "workload": f"{cfg['name']}: planning CT {int(geo.nVoxel[1])}x{int(geo.nVoxel[2])}x{int(geo.nVoxel[0])}, "
+                    f"{len(cfg['angles'])} projections of {int(geo.nDetector[1])}x{int(geo.nDetector[0])}"
+                    f"{' half-fan' if float(np.asarray(geo.offDetector)[1]) != 0 else ''}, scatter+noise, "
+                    f"{cfg['niter']}-iteration OS-SART (blocksize {cfg['blocksize']}, {nsub} subsets)",
+        "niter": cfg["niter"], "blocksize": cfg["blocksize"], "I0": cfg["I0"], "sigma": cfg["sigma"],
+        "accuracy": float(geo.accuracy),
+        "parallelism": "1 GPU" if n_gpus == 1 else
+                       f"angles of each subset interleaved over {n_gpus} GPUs, NCCL all-reduce of the update per subset",
+        "l2": "per-step working set (projections + volumes, ~2.4 GB at C2) exceeds the 126 MB L2; no flush",
+    }
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.path = None, None
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------- CPU baseline
+def cpu_sample(cfg, n_sample_angles=4):
+    """Time the oracle on a bounded sample of the workload: Ax + Atb of a few angles."""
+    from oracle import cpu_oracle
+    from physics_arx_b200.phantom import lung_phantom
+    cpu_oracle.build()
+    geo, angles = cfg["geo"], cfg["angles"]
+    n = len(angles)
+    pick = np.linspace(0, n, n_sample_angles, endpoint=False).astype(int)
+    vol = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0).astype(np.float64)
+    t0 = time.perf_counter()
+    proj = cpu_oracle.ax(vol, geo, angles[pick])
+    t1 = time.perf_counter()
+    cpu_oracle.atb(proj, geo, angles[pick])
+    t2 = time.perf_counter()
+    t_ax, t_atb = (t1 - t0) / len(pick), (t2 - t1) / len(pick)
+    # one volume = 1 simulation Ax + niter * (Ax + Atb) over all angles (V set-up not counted)
+    t_vol = n * t_ax + cfg["niter"] * n * (t_ax + t_atb)
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": 1.0 / t_vol, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"float64 oracle (oracle/oracle.c, OpenMP) Ax+Atb of {len(pick)} of the {n} angles at full "
+                      f"{cfg['name']} size: {t_ax:.2f} s/angle Ax, {t_atb:.2f} s/angle Atb; extrapolated to "
+                      f"1+{cfg['niter']} Ax and {cfg['niter']} Atb passes",
+            "t_ax_per_angle_s": t_ax, "t_atb_per_angle_s": t_atb}
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_sample(cfg, n_sample_angles=2)
+        if i >= args.warmup:
+            vals.append(info["value"])
+    v = float(np.mean(vals))
+    info["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": describe(cfg, args.gpus), "cpu_baseline": info,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference has no CPU implementation of this path (TIGRE is CUDA-only, un-vendored); "
+                    "this arm times the build's float64 oracle on the host cores, each step a bounded sample"}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C2", choices=["C1", "C2"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = get_config(args.config)
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+    if args.warmup < 3:
+        print("warning: fewer than 3 warm-up steps", file=sys.stderr)
+
+    import torch
+    import torch.distributed as dist
+    from physics_arx_b200 import _lib
+    from physics_arx_b200.phantom import artifact_volume, lung_phantom
+    from physics_arx_b200.pipeline import SCBCTPipeline
+
+    _lib.load()                      # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        group = dist.group.WORLD
+    if args.gpus != world and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    geo, angles = cfg["geo"], cfg["angles"]
+    ct_np = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    art_np = artifact_volume(geo.nVoxel, seed=1)
+    ct_host = torch.from_numpy(ct_np).pin_memory()
+    art_host = torch.from_numpy(art_np).pin_memory()
+    out_host = torch.empty(ct_host.shape, dtype=torch.float32).pin_memory()
+    ct_dev, art_dev = ct_host.cuda(), art_host.cuda()
+    pipe = SCBCTPipeline(geo, angles, niter=cfg["niter"], blocksize=cfg["blocksize"], I0=cfg["I0"],
+                         sigma=cfg["sigma"], scatter_scale=SCATTER_SCALE, seed=0, group=group)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        pipe.run_device(ct_dev, art_dev)
+    # exact trilinear-sample count of one full Ax pass over this rank's angles (untimed)
+    ns = torch.zeros(1, dtype=torch.int64, device="cuda")
+    if pipe.n_local:
+        pipe.plan.ax(pipe.ct_res, 0, pipe.n_local, out=pipe.st.b, nsamples=ns)
+    barrier()
+    samples_per_pass = int(ns.item())
+
+    # ---- timed region: K steps, inputs resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    pipe.launches = 0
+    pipe.st.kernel_events = []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pipe.run_device(ct_dev, art_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pipe.launches
+    events = pipe.st.kernel_events
+    pipe.st.kernel_events = None
+    ax_ms = [a.elapsed_time(b) for a, b, _ in events]
+    ax_counts = [c for _, _, c in events]
+    clocks = sampler.stop() if sampler else None
+
+    # ---- e2e: the public host-buffer call, copies inside the timed region
+    e2e_ms = None
+    if not args.no_e2e:
+        pipe.run_host(ct_host, art_host, out_host)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            pipe.run_host(ct_host, art_host, out_host)
+        f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, e2e_ms or 0.0, float(samples_per_pass), float(sum(ax_ms))], dtype=torch.float64,
+                     device="cuda")
+    tmax = t.clone()
+    tsum = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ln)
+        launches = int(ln.item())
+    ms = float(tmax[0].item())
+    e2e_ms = float(tmax[1].item()) if e2e_ms is not None else None
+    total_samples_per_pass = float(tsum[2].item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        nvox = int(np.prod(geo.nVoxel))
+        npix = int(np.prod(geo.nDetector))
+        # dominant kernel: k_ax in residual mode. algorithmic bytes per launch:
+        # read the volume once, read b and write W*(b-Ax) for the launch's angles.
+        avg_count = float(np.mean(ax_counts)) if ax_counts else 0.0
+        avg_ms = float(np.mean(ax_ms)) if ax_ms else float("nan")
+        alg_bytes = 4.0 * nvox + 8.0 * avg_count * npix
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if ax_ms else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
+                f"{cfg['name']}_ax_residual_bytes_per_launch")
+        except Exception:
+            pass
+        ax_share = float(sum(ax_ms)) / float(t[0].item()) if ax_ms else None
+        samples_resid = samples_per_pass * cfg["niter"] * args.steps     # rank 0's residual passes
+        line = {
+            "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": describe(cfg, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "k_ax<1,RESIDUAL,32>",
+                         "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                         "alg_bytes_per_launch": alg_bytes, "share_of_step": ax_share,
+                         "note": "gather-bound (L1 wavefronts / issue slots), not HBM-bound: see "
+                                 "ax_gsamples_per_s and profiles/"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "ax_gsamples_per_s": (samples_resid / (sum(ax_ms) * 1e-3) / 1e9) if ax_ms else None,
+            "ax_samples_per_full_pass": total_samples_per_pass,
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                           "h2d_bytes_per_step": int(ct_host.numel() * 4 + art_host.numel() * 4),
+                           "d2h_bytes_per_step": int(out_host.numel() * 4),
+                           "api": "SCBCTPipeline.run_host (pinned host volumes in, host volume out)"}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_sample(cfg)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,11 +51,16 @@ class OSSARTState:
         self.blocks = order_subsets(n, blocksize, OrderStrategy, seed)
         local, self.ranges = shard_blocks(self.blocks, self.rank, self.world)
         self.local_idx = local
-        dev = proj.device
+        dev = proj.device if proj is not None else torch.device(
+            "cuda", torch.cuda.current_device() if device is None else int(device))
         # a rank may own no angle at all (n < world): keep one dummy angle so a plan exists
         plan_idx = local if len(local) else np.array([0])
         self.plan = Plan(subset_geometry(geo, plan_idx, n), angles[plan_idx], device=dev.index)
-        if len(local) == n and np.array_equal(local, np.arange(n)):
+        if proj is None:                                    # caller fills the rank-local buffer
+            nv, nu = (int(v) for v in geo.nDetector)
+            self.b = torch.empty((max(len(local), 1), nv, nu), dtype=torch.float32,
+                                 device=dev)[:len(local)]
+        elif len(local) == n and np.array_equal(local, np.arange(n)):
             self.b = proj                                   # ordered, single rank: no copy
         else:
             self.b = proj[torch.as_tensor(local, device=dev, dtype=torch.long)].contiguous()
@@ -79,25 +84,37 @@ class OSSARTState:
         self.resid = torch.empty((max(self.max_count, 1), p.nv, p.nu), dtype=torch.float32, device=dev)
         self.upd = p.new_volume() if self.world > 1 else None
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.launches = 0              # kernels of libpax launched by subset_step (bench claim)
+        self.kernel_events = None      # set to [] to record CUDA events around the Ax kernel
 
     def subset_step(self, x_res, s, lam, noneg=True, computel2=False):
         import torch.distributed as dist
         p = self.plan
         first, count = self.ranges[s]
         ss = self.sumsq if computel2 else None
-        if self.world == 1:
+        if count:
+            ev = None
+            if self.kernel_events is not None:     # bench: time the dominant kernel in place
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             p.ax_residual(x_res, self.b[first:first + count], first, count, self.resid,
                           self.w_variant, ss)
+            if ev is not None:
+                ev[1].record()
+                self.kernel_events.append((ev[0], ev[1], count))
+            self.launches += 1
+        if self.world == 1:
             p.atb(self.resid, first, count, x_res, _lib.PAX_ATB_SART, self.inv_v[s], lam, noneg)
+            self.launches += 1
             return
         if count:
-            p.ax_residual(x_res, self.b[first:first + count], first, count, self.resid,
-                          self.w_variant, ss)
             p.atb(self.resid, first, count, self.upd, _lib.PAX_ATB_STORE)
+            self.launches += 1
         else:
             self.upd.zero_()
         dist.all_reduce(self.upd, group=self.group)
         p.sart_update(x_res, self.upd, self.inv_v[s], lam, noneg)
+        self.launches += 1
 
     def iteration(self, x_res, lam, noneg=True, computel2=False):
         for s in range(len(self.blocks)):

@@ -1,0 +1,158 @@
+"""The whole sCBCT generation loop of the reference, device-resident:
+
+    forward projection of (planning CT + scale * artifact volume)     [:86, AddImages.cxx:57-62]
+    -> Poisson + electronic noise                                      [:88]
+    -> OS-SART reconstruction                                          [:101-103]
+
+(file:line = Physics-based-Augmentation/OSSART-Reconstruction/pCT_CBCT_Reconstruction.py).
+One ``SCBCTPipeline`` holds the plan and every buffer for a (geometry, angle list); a run
+allocates nothing.  With a torch.distributed group the angles of each OS-SART subset are
+interleaved over the ranks: the simulation Ax and the noise need no
+collective beyond one scalar max, OS-SART all-reduces one partial volume update per subset.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .algorithms.ossart import OSSARTState
+from .projector import _ptr, _stream, reduce_max
+
+
+class SCBCTPipeline:
+    def __init__(self, geo, angles, niter=20, blocksize=20, I0=1e8, sigma=4.0, scatter_scale=1.0,
+                 lmbda=1.0, lmbda_red=0.99, seed=0, group=None, device=None, w_variant="matlab",
+                 v_variant="A"):
+        if not torch.cuda.is_available():
+            raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.geo = geo
+        self.angles = np.asarray(angles, dtype=np.float64)
+        self.niter, self.blocksize = int(niter), int(blocksize)
+        self.I0, self.sigma, self.scatter_scale = float(I0), float(sigma), float(scatter_scale)
+        self.lmbda, self.lmbda_red, self.seed = float(lmbda), float(lmbda_red), int(seed)
+        self.group = group
+        self.v_variant = v_variant
+        # OS-SART state with an empty rank-local projection buffer; simulate() fills st.b
+        with torch.cuda.device(self.device):
+            self.st = OSSARTState(None, geo, self.angles, blocksize, None, w_variant=w_variant,
+                                  v_variant=v_variant, group=group, distributed=group is not None,
+                                  device=self.device.index)
+        st = self.st
+        self.plan = st.plan
+        self.n_local = len(st.local_idx)
+        self.local_idx = st.local_idx
+        p = self.plan
+        self.ct_res = p.new_volume()
+        self.art_res = p.new_volume()
+        self.x_res = p.new_volume()
+        self.out = torch.empty((p.nz, p.ny, p.nx), dtype=torch.float32, device=self.device)
+        self.launches = 0
+
+    # ------------------------------------------------------------------ stages
+    def simulate(self, ct_dev, art_dev=None):
+        """Noisy projections of this rank's angles into st.b (device resident)."""
+        import torch.distributed as dist
+        p, st = self.plan, self.st
+        p.pack(ct_dev, out=self.ct_res)
+        self.launches += 1
+        res1 = None
+        if art_dev is not None:
+            p.pack(art_dev, out=self.art_res)
+            self.launches += 1
+            res1 = self.art_res
+        if self.n_local:
+            p.ax(self.ct_res, 0, self.n_local, out=st.b, res1=res1, a0=1.0, a1=self.scatter_scale)
+            self.launches += 1
+        m = reduce_max(st.b) if self.n_local else torch.full((1,), -3e38, device=self.device)
+        self.launches += 2
+        if self.group is not None:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+        # noise is keyed by the GLOBAL pixel index, so the result does not depend on the sharding
+        npix = p.nv * p.nu
+        lib = p.lib
+        runs = _contiguous_runs(self.local_idx)
+        pos = 0
+        with torch.cuda.device(self.device):
+            for g0, cnt in runs:
+                view = st.b[pos:pos + cnt]
+                _lib.check(lib.pax_ctnoise(_ptr(view), view.numel(), ctypes.c_uint64(int(g0) * npix),
+                                           self.I0, 0.0, self.sigma, _ptr(m),
+                                           ctypes.c_uint64(self.seed), _stream()), "pax_ctnoise")
+                self.launches += 1
+                pos += cnt
+        return st.b
+
+    def reconstruct(self):
+        st = self.st
+        p = self.plan
+        if self.v_variant == "A":      # set_v runs inside every ossart() call of the reference
+            import torch.distributed as dist
+            V = torch.zeros_like(st.inv_v)
+            for s, (first, count) in enumerate(st.ranges):
+                if count:
+                    p.compute_v(first, count, out=V[s])
+                    self.launches += 1
+            if st.world > 1:
+                dist.all_reduce(V, group=st.group)
+            st.inv_v = torch.where(V > 1e-12, 1.0 / V, torch.zeros_like(V)).contiguous()
+        self.x_res.zero_()
+        lam = self.lmbda
+        n0 = st.launches
+        for _ in range(self.niter):
+            st.iteration(self.x_res, lam, True, False)
+            lam *= self.lmbda_red
+        self.launches += st.launches - n0
+        p.unpack(self.x_res, out=self.out)
+        self.launches += 1
+        return self.out
+
+    # ------------------------------------------------------------- entry points
+    def run_device(self, ct_dev, art_dev=None):
+        """Inputs already in HBM -> reconstructed (Z,Y,X) volume in HBM."""
+        with torch.cuda.device(self.device):
+            self.simulate(ct_dev, art_dev)
+            return self.reconstruct()
+
+    def run_host(self, ct_host, art_host=None, out_host=None):
+        """Host buffers in -> host volume out (the call a user of the reference script makes)."""
+        with torch.cuda.device(self.device):
+            ct = _as_tensor(ct_host).to(self.device, non_blocking=True)
+            art = _as_tensor(art_host).to(self.device, non_blocking=True) if art_host is not None else None
+            out = self.run_device(ct, art)
+            if out_host is None:
+                out_host = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
+            out_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out_host
+
+
+def _contiguous_runs(idx):
+    """[(global_first_angle, count)] covering a sorted-by-subset local index list."""
+    runs = []
+    for g in np.asarray(idx):
+        g = int(g)
+        if runs and runs[-1][0] + runs[-1][1] == g:
+            runs[-1][1] += 1
+        else:
+            runs.append([g, 1])
+    return [(a, b) for a, b in runs]
+
+
+def _as_tensor(a):
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float32:
+            raise TypeError("host volumes must be float32")
+        return torch.from_numpy(np.ascontiguousarray(a))
+    return a
+
+
+def generate_scbct(ct, geo, angles, artifact=None, scatter_scale=1.0, I0=1e8, sigma=4.0, niter=30,
+                   blocksize=20, seed=0, **kw):
+    """One-call form: NumPy (Z,Y,X) planning CT [+ artifact volume] -> NumPy sCBCT volume."""
+    pipe = SCBCTPipeline(geo, angles, niter=niter, blocksize=blocksize, I0=I0, sigma=sigma,
+                         scatter_scale=scatter_scale, seed=seed, **kw)
+    return pipe.run_host(ct, artifact).numpy().copy()
