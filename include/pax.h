@@ -101,9 +101,13 @@ int pax_vol_pack(const PaxPlan *plan, const float *vol_zyx, float *vol_res, void
 int pax_vol_unpack(const PaxPlan *plan, const float *vol_res, float *vol_zyx, void *stream);
 
 /* tigre.Ax(img, geo, angles, 'interpolated')  -- reference :86; angles [first, first+count)
- * of the plan; vol_res1 may be NULL (single channel). proj_out is (count,V,U). */
+ * of the plan; vol_res1 may be NULL (single channel). proj_out is (count,V,U).
+ * workspace: device scratch of pax_ax_workspace_bytes(plan, channels) bytes, 16-byte aligned,
+ * that receives the gather-friendly re-packing of the volume(s) for this call; NULL selects
+ * the slower kernel that gathers from the resident layout directly. */
+size_t pax_ax_workspace_bytes(const PaxPlan *plan, int n_channels);
 int pax_ax(const PaxPlan *plan, const float *vol_res0, const float *vol_res1, int first, int count,
-           float *proj_out, const PaxAxEpilogue *epi, void *stream);
+           float *proj_out, const PaxAxEpilogue *epi, void *workspace, void *stream);
 
 /* tigre.Atb(proj, geo, angles, 'FDK')  -- reached via ossart, reference :103.
  * proj is (count,V,U) for angles [first, first+count); vol_res is in resident layout. */

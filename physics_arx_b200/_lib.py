@@ -47,8 +47,9 @@ SYMBOLS = [
     ("pax_vol_elems", ctypes.c_size_t, [_VP]),
     ("pax_vol_pack", ctypes.c_int, [_VP, _VP, _VP, _VP]),
     ("pax_vol_unpack", ctypes.c_int, [_VP, _VP, _VP, _VP]),
+    ("pax_ax_workspace_bytes", ctypes.c_size_t, [_VP, ctypes.c_int]),
     ("pax_ax", ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
-                              ctypes.POINTER(PaxAxEpilogue), _VP]),
+                              ctypes.POINTER(PaxAxEpilogue), _VP, _VP]),
     ("pax_atb", ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
                                ctypes.POINTER(PaxAtbEpilogue), _VP]),
     ("pax_sart_update", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_float, ctypes.c_int, _VP]),

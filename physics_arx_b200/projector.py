@@ -11,6 +11,7 @@ in libpax.so (csrc/), called through the C ABI of include/pax.h.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -64,6 +65,8 @@ class Plan:
                                                 self.n_angles, ctypes.byref(handle)), "pax_plan_create")
         self._h = handle
         self.vol_elems = int(self.lib.pax_vol_elems(self._h))
+        self._work = None              # Ax scratch (quad-packed volume), grown on demand
+        self.use_workspace = os.environ.get("PAX_AX_KERNEL", "quad") != "plain"
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -100,6 +103,14 @@ class Plan:
             _lib.check(self.lib.pax_vol_unpack(self._h, _ptr(res), _ptr(out), _stream()), "pax_vol_unpack")
         return out
 
+    def _workspace(self, channels):
+        if not self.use_workspace:
+            return None
+        need = int(self.lib.pax_ax_workspace_bytes(self._h, channels))
+        if self._work is None or self._work.numel() * 4 < need:
+            self._work = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+        return self._work
+
     # --------------------------------------------------------------- projectors
     def _w_box(self, w_variant):
         (hz, hy, hx), thr = self.geo.w_box(w_variant)
@@ -116,7 +127,8 @@ class Plan:
                                  nsamples.data_ptr() if nsamples is not None else None)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_ax(self._h, _ptr(res0), _ptr(res1), first, count, _ptr(out),
-                                       ctypes.byref(epi), _stream()), "pax_ax")
+                                       ctypes.byref(epi), _ptr(self._workspace(1 if res1 is None else 2)),
+                                       _stream()), "pax_ax")
         return out
 
     def ax_residual(self, res, b, first, count, out, w_variant="matlab", sumsq=None):
@@ -126,7 +138,7 @@ class Plan:
                                  sumsq.data_ptr() if sumsq is not None else None, None)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_ax(self._h, _ptr(res), None, first, count, _ptr(out),
-                                       ctypes.byref(epi), _stream()), "pax_ax")
+                                       ctypes.byref(epi), _ptr(self._workspace(1)), _stream()), "pax_ax")
         return out
 
     def atb(self, proj, first, count, out_res, mode=_lib.PAX_ATB_STORE, inv_v=None, lam=1.0, noneg=True):
