@@ -23,6 +23,8 @@
 //                   for A/B measurement, selected when no workspace is given).
 // CTAs are ordered u-tile fastest, then angle, then v-tile: all angles of a launch that
 // look at the same z slab of the volume run together, so the slab stays in the 126 MB L2.
+#include <cstdlib>
+
 #include "pax_internal.h"
 
 struct AxArgs {
@@ -133,13 +135,13 @@ __device__ __forceinline__ void ax_sample_quad(const float4 *__restrict__ q0,
 }
 
 // LV = detector rows per warp (32/LV columns).  8 warps per CTA, stacked along u.
-template <int NCH, int MODE, int LV, bool QUAD>
-__global__ void __launch_bounds__(256) k_ax(const AxArgs a)
+template <int NCH, int MODE, int LV, bool QUAD, int NW, int MINB, int UNR>
+__global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
 {
     constexpr int LU = 32 / LV;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int v = blockIdx.z * LV + (lane % LV);
-    const int u = (blockIdx.x * 8 + warp) * LU + lane / LV;
+    const int u = (blockIdx.x * NW + warp) * LU + lane / LV;
     const int ia = blockIdx.y;
     const bool live = (u < a.nu) && (v < a.nv);
     const AngleDev &A = a.angles[a.first + ia];
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256) k_ax(const AxArgs a)
                 const unsigned kfold = (unsigned)AX_MAGIC_I * (sy + sx + 1u);
                 const float2 exy = make_float2(ex, ey), dxy = make_float2(fdx, fdy);
                 float fj = (float)j0;
-#pragma unroll 4
+#pragma unroll UNR
                 for (int j = j0; j < ns; ++j) {
                     ax_sample_quad<NCH>(q0, q1, __ffma2_rn(make_float2(fj, fj), dxy, exy),
                                         fmaf(fj, fdz, ez), sx, sy, kfold, s0, s1);
@@ -245,16 +247,16 @@ __global__ void __launch_bounds__(256) k_ax(const AxArgs a)
     }
 }
 
-template <int NCH, int MODE, bool QUAD>
+template <int NCH, int MODE, bool QUAD, int NW = 8, int MINB = 6, int UNR = 4>
 static void launch_ax(const AxArgs &a, int count, cudaStream_t st)
 {
     // rows-per-warp: tall detectors get the full 32-row column warp; short ones fall back
     if (a.nv >= 32) {
-        dim3 grid(pax_cdiv(a.nu, 8), count, pax_cdiv(a.nv, 32));
-        k_ax<NCH, MODE, 32, QUAD><<<grid, 256, 0, st>>>(a);
+        dim3 grid(pax_cdiv(a.nu, NW), count, pax_cdiv(a.nv, 32));
+        k_ax<NCH, MODE, 32, QUAD, NW, MINB, UNR><<<grid, NW * 32, 0, st>>>(a);
     } else {
-        dim3 grid(pax_cdiv(a.nu, 32), count, pax_cdiv(a.nv, 8));
-        k_ax<NCH, MODE, 8, QUAD><<<grid, 256, 0, st>>>(a);
+        dim3 grid(pax_cdiv(a.nu, NW * 4), count, pax_cdiv(a.nv, 8));
+        k_ax<NCH, MODE, 8, QUAD, NW, MINB, UNR><<<grid, NW * 32, 0, st>>>(a);
     }
 }
 
@@ -315,8 +317,20 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
         k_quad_pack<<<blocks, 256, 0, st>>>(vol_res0, q, nyq, nxq, p->nxp, p->nzp);
         if (vol_res1) k_quad_pack<<<blocks, 256, 0, st>>>(vol_res1, q + per, nyq, nxq, p->nxp, p->nzp);
         a.quad0 = q; a.quad1 = vol_res1 ? q + per : nullptr; a.qsy = nxq * p->nzp;
-        if (epi->mode == PAX_AX_RESIDUAL) launch_ax<1, PAX_AX_RESIDUAL, true>(a, count, st);
-        else if (vol_res1) launch_ax<2, PAX_AX_PLAIN, true>(a, count, st);
+        if (epi->mode == PAX_AX_RESIDUAL) {
+            const char *ev = getenv("PAX_AX_VARIANT");      // tuning hook (tools/profile_step.py)
+            switch (ev ? atoi(ev) : 0) {
+            case 1: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 4, 4>(a, count, st); break;
+            case 2: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 3, 8>(a, count, st); break;
+            case 3: launch_ax<1, PAX_AX_RESIDUAL, true, 4, 8, 4>(a, count, st); break;
+            case 4: launch_ax<1, PAX_AX_RESIDUAL, true, 4, 12, 4>(a, count, st); break;
+            case 5: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 5, 2>(a, count, st); break;
+            case 6: launch_ax<1, PAX_AX_RESIDUAL, true, 16, 2, 4>(a, count, st); break;
+            case 7: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 1, 4>(a, count, st); break;
+            case 8: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 2, 8>(a, count, st); break;
+            default: launch_ax<1, PAX_AX_RESIDUAL, true>(a, count, st); break;
+            }
+        } else if (vol_res1) launch_ax<2, PAX_AX_PLAIN, true>(a, count, st);
         else launch_ax<1, PAX_AX_PLAIN, true>(a, count, st);
     } else {
         a.quad0 = a.quad1 = nullptr; a.qsy = 0;
