@@ -70,6 +70,9 @@ typedef struct PaxAxEpilogue {
     float w_thr;                    /* chord lengths <= w_thr give W = 0 */
     double *sumsq;                  /* optional device scalar: += sum (b-P0)^2 (computel2) */
     unsigned long long *nsamples;   /* optional device scalar: += trilinear samples taken */
+    uint32_t *maxout;               /* optional device word (PLAIN): running max of out, order-encoded;
+                                       zero it first, finish with pax_max_decode -- the normalising
+                                       max of CTnoise.add fused into the projection epilogue */
 } PaxAxEpilogue;
 
 /* What the backprojector does with the accumulated sum  acc = sum_angles w * bilinear(proj):
@@ -100,6 +103,10 @@ size_t pax_vol_elems(const PaxPlan *plan);
 int pax_vol_pack(const PaxPlan *plan, const float *vol_zyx, float *vol_res, void *stream);
 int pax_vol_unpack(const PaxPlan *plan, const float *vol_res, float *vol_zyx, void *stream);
 
+/* y += a*x on two volumes in resident layout: the reference's image-domain scatter transfer
+ * (AddImages.cxx:57-62, pCT + artifact) when only one variation is wanted. */
+int pax_vol_axpy(const PaxPlan *plan, float *y_res, const float *x_res, float a, void *stream);
+
 /* tigre.Ax(img, geo, angles, 'interpolated')  -- reference :86; angles [first, first+count)
  * of the plan; vol_res1 may be NULL (single channel). proj_out is (count,V,U).
  * workspace: device scratch of pax_ax_workspace_bytes(plan, channels) bytes, 16-byte aligned,
@@ -127,6 +134,8 @@ int pax_compute_v(const PaxPlan *plan, int first, int count, double vscale, floa
 
 /* max over n floats -> *out_dev (device float) */
 int pax_reduce_max(const float *x, size_t n, float *out_dev, void *stream);
+/* turn the order-encoded running max of PaxAxEpilogue.maxout into a float, in place */
+int pax_max_decode(uint32_t *word_dev, void *stream);
 
 /* tigre.utilities.CTnoise.add -- reference :88.  In place on n floats whose global
  * element index starts at index0 (noise is a function of (seed, global index) only, so

@@ -38,6 +38,7 @@ struct AxArgs {
     const float *b;
     double *sumsq;
     unsigned long long *nsamples;
+    unsigned *maxout;
     int first, nv, nu;
     int nxp, nzp;                 // resident strides: x -> nzp, y -> nxp*nzp
     float hix, hiy, hiz;          // exclusive upper bounds of valid padded coordinates
@@ -177,15 +178,29 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
         if (hit && t0 <= t1) {
             const double i0 = ceil(t0), i1 = floor(t1);
             ns = (int)(i1 - i0) + 1;
-            const float ex = (float)(A.sx + i0 * dx), ey = (float)(A.sy + i0 * dy),
-                        ez = (float)(A.sz + i0 * dz);
             const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz;
+            // Four interleaved sub-lattices: sample j sits at E[j&3] + (j & ~3) * d with the origins
+            // E[k] = S + (i0+k) d rounded from double.  One counter update per four samples, and no
+            // rounding accumulates along the ray.
+            float2 exy[4];
+            float ezk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double jk = i0 + (double)k;
+                exy[k] = make_float2((float)(A.sx + jk * dx), (float)(A.sy + jk * dy));
+                ezk[k] = (float)(A.sz + jk * dz);
+            }
+            const float ex = exy[0].x, ey = exy[0].y, ez = ezk[0];
             // the fp32 positions of the first/last sample must themselves be in range
             // (the march does no bounds checks): trim the ends if rounding pushed them out.
             int j0 = 0;
             auto inside = [&](int j) {
-                const float qx = fmaf((float)j, fdx, ex), qy = fmaf((float)j, fdy, ey),
-                            qz = fmaf((float)j, fdz, ez);
+                const float fb = (float)(j & ~3);
+                const int k = j & 3;
+                const float bx = k == 0 ? exy[0].x : k == 1 ? exy[1].x : k == 2 ? exy[2].x : exy[3].x;
+                const float by = k == 0 ? exy[0].y : k == 1 ? exy[1].y : k == 2 ? exy[2].y : exy[3].y;
+                const float bz = k == 0 ? ezk[0] : k == 1 ? ezk[1] : k == 2 ? ezk[2] : ezk[3];
+                const float qx = fmaf(fb, fdx, bx), qy = fmaf(fb, fdy, by), qz = fmaf(fb, fdz, bz);
                 return qx >= 0.f && qx < a.hix && qy >= 0.f && qy < a.hiy && qz >= a.loz && qz < a.hiz;
             };
             while (j0 < ns && !inside(j0)) ++j0;
@@ -195,23 +210,46 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
                 const float4 *__restrict__ q1 = a.quad1;
                 const unsigned sx = (unsigned)a.nzp, sy = (unsigned)a.qsy;
                 const unsigned kfold = (unsigned)AX_MAGIC_I * (sy + sx + 1u);
-                const float2 exy = make_float2(ex, ey), dxy = make_float2(fdx, fdy);
-                float fj = (float)j0;
-#pragma unroll UNR
-                for (int j = j0; j < ns; ++j) {
-                    ax_sample_quad<NCH>(q0, q1, __ffma2_rn(make_float2(fj, fj), dxy, exy),
-                                        fmaf(fj, fdz, ez), sx, sy, kfold, s0, s1);
-                    fj += 1.f;
+                const float2 dxy = make_float2(fdx, fdy);
+                int j = j0;
+                // head: up to the next multiple of four
+                for (; (j & 3) && j < ns; ++j) {
+                    const float fb = (float)(j & ~3);
+                    const int k = j & 3;
+                    const float2 e = k == 1 ? exy[1] : k == 2 ? exy[2] : exy[3];
+                    const float z = k == 1 ? ezk[1] : k == 2 ? ezk[2] : ezk[3];
+                    ax_sample_quad<NCH>(q0, q1, __ffma2_rn(make_float2(fb, fb), dxy, e), fmaf(fb, fdz, z), sx, sy,
+                                        kfold, s0, s1);
+                }
+                float fm = (float)j;
+#pragma unroll 1
+                for (; j + 4 <= ns; j += 4) {
+                    const float2 fm2 = make_float2(fm, fm);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ax_sample_quad<NCH>(q0, q1, __ffma2_rn(fm2, dxy, exy[k]), fmaf(fm, fdz, ezk[k]), sx,
+                                            sy, kfold, s0, s1);
+                    fm += 4.f;
+                }
+                for (int k = 0; j < ns; ++j, ++k) {
+                    const float2 e = k == 0 ? exy[0] : k == 1 ? exy[1] : exy[2];
+                    const float z = k == 0 ? ezk[0] : k == 1 ? ezk[1] : ezk[2];
+                    ax_sample_quad<NCH>(q0, q1, __ffma2_rn(make_float2(fm, fm), dxy, e), fmaf(fm, fdz, z), sx, sy,
+                                        kfold, s0, s1);
                 }
             } else {
                 const float *__restrict__ v0 = a.vol0;
                 const float *__restrict__ v1 = a.vol1;
                 const int sx = a.nzp, sy = a.nxp * a.nzp;
+                (void)ex; (void)ey; (void)ez;
 #pragma unroll 2
                 for (int j = j0; j < ns; ++j) {
-                    const float fj = (float)j;
-                    ax_sample<NCH>(v0, v1, fmaf(fj, fdx, ex), fmaf(fj, fdy, ey), fmaf(fj, fdz, ez), sx,
-                                   sy, s0, s1);
+                    const float fb = (float)(j & ~3);
+                    const int k = j & 3;
+                    const float2 e = k == 0 ? exy[0] : k == 1 ? exy[1] : k == 2 ? exy[2] : exy[3];
+                    const float z = k == 0 ? ezk[0] : k == 1 ? ezk[1] : k == 2 ? ezk[2] : ezk[3];
+                    ax_sample<NCH>(v0, v1, fmaf(fb, fdx, e.x), fmaf(fb, fdy, e.y), fmaf(fb, fdz, z), sx, sy,
+                                   s0, s1);
                 }
             }
             ns -= j0;
@@ -219,7 +257,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
             steplen = sqrtf(mx * mx + my * my + mz * mz);
         }
     }
-    float r2 = 0.f;
+    float r2 = 0.f, mymax = -INFINITY;
     if (live) {
         const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
         const float p0 = s0 * steplen;
@@ -228,6 +266,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
             if (NCH == 2) val = fmaf(a.a1, s1 * steplen, val);
             if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
             a.out[o] = val;
+            mymax = val;
         } else {
             const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
             const float w = L > a.wthr ? 1.f / L : 0.f;
@@ -241,13 +280,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
         t = __reduce_add_sync(0xffffffffu, t);
         if (lane == 0 && t) atomicAdd(a.nsamples, (unsigned long long)t);
     }
+    if (MODE == PAX_AX_PLAIN && a.maxout) {
+        for (int o = 16; o; o >>= 1) mymax = fmaxf(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+        if (lane == 0) {
+            const unsigned b = __float_as_uint(mymax);
+            atomicMax(a.maxout, (b & 0x80000000u) ? ~b : (b | 0x80000000u));
+        }
+    }
     if (MODE == PAX_AX_RESIDUAL && a.sumsq) {
         for (int o = 16; o; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
         if (lane == 0) atomicAdd(a.sumsq, (double)r2);
     }
 }
 
-template <int NCH, int MODE, bool QUAD, int NW = 8, int MINB = 6, int UNR = 4>
+template <int NCH, int MODE, bool QUAD, int NW = 8, int MINB = 4, int UNR = 4>
 static void launch_ax(const AxArgs &a, int count, cudaStream_t st)
 {
     // rows-per-warp: tall detectors get the full 32-row column warp; short ones fall back
@@ -297,7 +343,7 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
     AxArgs a;
     a.angles = p->d_angles;
     a.vol0 = vol_res0; a.vol1 = vol_res1; a.out = proj_out; a.b = epi->b;
-    a.sumsq = epi->sumsq; a.nsamples = epi->nsamples;
+    a.sumsq = epi->sumsq; a.nsamples = epi->nsamples; a.maxout = epi->maxout;
     a.first = first; a.nv = p->geo.nDetecV; a.nu = p->geo.nDetecU;
     a.nxp = p->nxp; a.nzp = p->nzp;
     a.hix = (float)(p->geo.nVoxelX + 1); a.hiy = (float)(p->geo.nVoxelY + 1);

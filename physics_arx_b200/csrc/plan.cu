@@ -259,6 +259,37 @@ extern "C" int pax_reduce_max(const float *x, size_t n, float *out_dev, void *st
     return PAX_OK;
 }
 
+extern "C" int pax_max_decode(uint32_t *word_dev, void *stream)
+{
+    PAX_REQUIRE(word_dev, "pax_max_decode: NULL argument");
+    k_max_decode<<<1, 1, 0, (cudaStream_t)stream>>>(word_dev);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
+__global__ void __launch_bounds__(256) k_axpy(float4 *__restrict__ y, const float4 *__restrict__ x, float a,
+                                              size_t n4)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = y[i];
+        const float4 w = x[i];
+        v.x = fmaf(a, w.x, v.x); v.y = fmaf(a, w.y, v.y); v.z = fmaf(a, w.z, v.z); v.w = fmaf(a, w.w, v.w);
+        y[i] = v;
+    }
+}
+
+// the rim of both operands is zero, so running over the whole padded array keeps it zero
+extern "C" int pax_vol_axpy(const PaxPlan *p, float *y_res, const float *x_res, float a, void *stream)
+{
+    PAX_REQUIRE(p && y_res && x_res, "pax_vol_axpy: NULL argument");
+    PAX_REQUIRE((((uintptr_t)y_res | (uintptr_t)x_res) & 15) == 0, "pax_vol_axpy: volumes must be 16-byte aligned");
+    const size_t n4 = p->vol_elems / 4;      // nzp is a multiple of 4
+    k_axpy<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(y_res),
+                                                      reinterpret_cast<const float4 *>(x_res), a, n4);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
 // ------------------------------------------------------------------------------ noise
 // Philox4x32-10 (Salmon et al. 2011), one block of 4 words per projection pixel keyed by
 // (seed, global pixel index); same word assignment as oracle_ctnoise.

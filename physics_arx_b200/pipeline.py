@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .algorithms.ossart import OSSARTState
-from .projector import _ptr, _stream, reduce_max
+from .projector import _ptr, _stream
 
 
 class SCBCTPipeline:
@@ -51,6 +51,7 @@ class SCBCTPipeline:
         self.x_res = p.new_volume()
         self.out = torch.empty((p.nz, p.ny, p.nx), dtype=torch.float32, device=self.device)
         self.launches = 0
+        self._max = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ stages
     def simulate(self, ct_dev, art_dev=None):
@@ -59,16 +60,19 @@ class SCBCTPipeline:
         p, st = self.plan, self.st
         p.pack(ct_dev, out=self.ct_res)
         self.launches += 1
-        res1 = None
         if art_dev is not None:
+            # one variation: add the artifact volume in the image domain (what the reference does,
+            # AddImages.cxx:57-62) and project one channel.  The two-channel epilogue
+            # (Plan.ax(res1=..., a1=...)) is for fanning several scatter scales out of one pass.
             p.pack(art_dev, out=self.art_res)
-            self.launches += 1
-            res1 = self.art_res
+            p.axpy(self.ct_res, self.art_res, self.scatter_scale)
+            self.launches += 2
+        m = self._max
         if self.n_local:
-            p.ax(self.ct_res, 0, self.n_local, out=st.b, res1=res1, a0=1.0, a1=self.scatter_scale)
-            self.launches += 1
-        m = reduce_max(st.b) if self.n_local else torch.full((1,), -3e38, device=self.device)
-        self.launches += 2
+            p.ax(self.ct_res, 0, self.n_local, out=st.b, maxout=m)     # max(p) fused in the epilogue
+            self.launches += 3                                          # quad pack, projector, decode
+        else:
+            m.fill_(-3e38)
         if self.group is not None:
             dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
         # noise is keyed by the GLOBAL pixel index, so the result does not depend on the sharding

@@ -116,26 +116,38 @@ class Plan:
         (hz, hy, hx), thr = self.geo.w_box(w_variant)
         return float(hz), float(hy), float(hx), float(thr)
 
+    def axpy(self, y_res, x_res, a):
+        """y_res += a * x_res (resident layout): image-domain scatter transfer, AddImages.cxx:57-62."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pax_vol_axpy(self._h, _ptr(y_res), _ptr(x_res), float(a), _stream()),
+                       "pax_vol_axpy")
+        return y_res
+
     def ax(self, res0, first=0, count=None, out=None, res1=None, a0=1.0, a1=0.0, c=0.0,
-           w_variant="matlab", nsamples=None):
+           w_variant="matlab", nsamples=None, maxout=None):
         """out[(count,V,U)] = a0*Ax(res0) + a1*Ax(res1) + c*chord.  (PAX_AX_PLAIN)"""
         count = self.n_angles - first if count is None else count
         if out is None:
             out = torch.empty((count, self.nv, self.nu), dtype=torch.float32, device=self.device)
         hz, hy, hx, thr = self._w_box(w_variant)
         epi = _lib.PaxAxEpilogue(_lib.PAX_AX_PLAIN, a0, a1, c, None, hz, hy, hx, thr, None,
-                                 nsamples.data_ptr() if nsamples is not None else None)
+                                 nsamples.data_ptr() if nsamples is not None else None,
+                                 maxout.data_ptr() if maxout is not None else None)
+        if maxout is not None:
+            maxout.zero_()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_ax(self._h, _ptr(res0), _ptr(res1), first, count, _ptr(out),
                                        ctypes.byref(epi), _ptr(self._workspace(1 if res1 is None else 2)),
                                        _stream()), "pax_ax")
+            if maxout is not None:    # maxout: 1-element float32 tensor, holds max(out) afterwards
+                _lib.check(self.lib.pax_max_decode(_ptr(maxout), _stream()), "pax_max_decode")
         return out
 
     def ax_residual(self, res, b, first, count, out, w_variant="matlab", sumsq=None):
         """out = W * (b - Ax(res)) for angles [first, first+count).  (PAX_AX_RESIDUAL)"""
         hz, hy, hx, thr = self._w_box(w_variant)
         epi = _lib.PaxAxEpilogue(_lib.PAX_AX_RESIDUAL, 1.0, 0.0, 0.0, b.data_ptr(), hz, hy, hx, thr,
-                                 sumsq.data_ptr() if sumsq is not None else None, None)
+                                 sumsq.data_ptr() if sumsq is not None else None, None, None)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_ax(self._h, _ptr(res), None, first, count, _ptr(out),
                                        ctypes.byref(epi), _ptr(self._workspace(1)), _stream()), "pax_ax")

@@ -146,3 +146,40 @@ def test_torch_tensor_roundtrip_stays_on_device():
     assert isinstance(p, torch.Tensor) and p.is_cuda
     x = pax.Atb(p, geo, angles, "FDK")
     assert isinstance(x, torch.Tensor) and x.is_cuda and tuple(x.shape) == shape
+
+
+def test_pipeline_fused_max_and_image_domain_scatter(oracle):
+    """SCBCTPipeline.simulate: max(p) from the Ax epilogue == max of the stored projections, and
+    pack+axpy+Ax == oracle Ax(ct + s*art) (the reference's AddImages -> Ax order)."""
+    torch = _torch()
+    from physics_arx_b200.phantom import artifact_volume, lung_phantom
+    from physics_arx_b200.pipeline import SCBCTPipeline
+    _, geo, angles = _cases()[1]
+    ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    art = artifact_volume(geo.nVoxel, seed=1)
+    pipe = SCBCTPipeline(geo, angles, niter=1, blocksize=4, I0=1e8, sigma=0.0, scatter_scale=0.7)
+    p = pipe.plan
+    p.pack(torch.from_numpy(ct).cuda(), out=pipe.ct_res)
+    p.pack(torch.from_numpy(art).cuda(), out=pipe.art_res)
+    p.axpy(pipe.ct_res, pipe.art_res, 0.7)
+    m = torch.zeros(1, device="cuda")
+    proj = p.ax(pipe.ct_res, maxout=m)
+    assert float(m.item()) == float(proj.max().item())
+    ref = oracle.ax(ct.astype(np.float64) + 0.7 * art.astype(np.float64), geo, angles)
+    assert rel_l2(proj.cpu().numpy(), ref) <= PROJ_TOL
+
+
+def test_plain_and_quad_gather_backends_agree(oracle):
+    """The workspace-less kernel (PAX_AX_KERNEL=plain) is the same arithmetic on the same lattice."""
+    torch = _torch()
+    from physics_arx_b200.projector import Plan
+    _, geo, angles = _cases()[1]
+    rng = np.random.default_rng(5)
+    vol = torch.from_numpy(rng.random(tuple(int(v) for v in geo.nVoxel)).astype(np.float32)).cuda()
+    plan = Plan(geo, angles)
+    res = plan.pack(vol)
+    a = plan.ax(res).cpu().numpy()
+    plan.use_workspace = False
+    b = plan.ax(res).cpu().numpy()
+    assert rel_l2(a, b) <= 2e-6
+    assert rel_l2(a, oracle.ax(vol.cpu().numpy(), geo, angles)) <= PROJ_TOL
