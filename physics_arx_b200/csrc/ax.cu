@@ -31,9 +31,10 @@ struct AxArgs {
     const AngleDev *angles;
     const float *vol0;
     const float *vol1;
-    const float4 *quad0;
-    const float4 *quad1;
-    int qsy;                      // quad stride of +1 in y ( (nxp-1)*nzp ); +1 in x is nzp
+    const char *quad0;            // quad-packed channels
+    const char *quad1;
+    int qshift;                   // log2 of the quad column stride in bytes
+    float nxq_f;                  // quad columns per y row
     float *out;
     const float *b;
     double *sumsq;
@@ -110,26 +111,32 @@ __device__ __forceinline__ float quad_trilinear(const float4 lo, const float4 hi
     return fmaf(fx, b.y - b.x, b.x);
 }
 
+// Address arithmetic without integer multiplies (IMAD is half rate on the FMA pipes, which bound
+// this kernel): the quad columns are padded to a power-of-two byte stride 2^qshift, the column
+// number cy*nxq + cx is formed by ONE FFMA on the (exactly integral) floats, landing biased by 2^23
+// in a mantissa, and the biases cancel in 32-bit modular arithmetic.  Shifts and adds go to the
+// otherwise idle ALU pipe.
 template <int NCH>
-__device__ __forceinline__ void ax_sample_quad(const float4 *__restrict__ q0,
-                                               const float4 *__restrict__ q1, float2 qxy, float qz,
-                                               unsigned sx, unsigned sy, unsigned kfold, float &s0,
-                                               float &s1)
+__device__ __forceinline__ void ax_sample_quad(const char *__restrict__ b0, const char *__restrict__ b1,
+                                               float2 qxy, float qz, float nxq_f, int qshift,
+                                               unsigned kbias, float &s0, float &s1)
 {
     const float2 mg = make_float2(AX_MAGIC, AX_MAGIC);
     const float2 txy = f2_add_rm(qxy, mg);
     const float tz = __fadd_rd(qz, AX_MAGIC);
-    const float2 fxy = f2_sub(qxy, f2_sub(txy, mg));
+    const float2 cxy = f2_sub(txy, mg);                  // (cx, cy): exact small integers
+    const float2 fxy = f2_sub(qxy, cxy);
     const float fz = qz - (tz - AX_MAGIC);
-    // the 2^23 bias of all three mantissas is folded into one constant (mod 2^32)
-    const unsigned lin = __float_as_uint(txy.y) * sy + __float_as_uint(txy.x) * sx + __float_as_uint(tz) - kfold;
+    const float col = fmaf(cxy.y, nxq_f, txy.x);         // cy*nxq + cx + 2^23, exact (< 2^24)
+    // 32-bit modular arithmetic: the biases cancel mod 2^32, the true byte offset is < 4 GB
+    const unsigned off = (__float_as_uint(col) << qshift) + (__float_as_uint(tz) << 4) - kbias;
     {
-        const float4 *p = q0 + lin;
+        const float4 *p = reinterpret_cast<const float4 *>(b0 + off);
         const float4 lo = __ldg(p), hi = __ldg(p + 1);
         s0 += quad_trilinear(lo, hi, fxy.x, fxy.y, fz);
     }
     if (NCH == 2) {
-        const float4 *p = q1 + lin;
+        const float4 *p = reinterpret_cast<const float4 *>(b1 + off);
         const float4 lo = __ldg(p), hi = __ldg(p + 1);
         s1 += quad_trilinear(lo, hi, fxy.x, fxy.y, fz);
     }
@@ -206,10 +213,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
             while (j0 < ns && !inside(j0)) ++j0;
             while (ns > j0 && !inside(ns - 1)) --ns;
             if (QUAD) {
-                const float4 *__restrict__ q0 = a.quad0;
-                const float4 *__restrict__ q1 = a.quad1;
-                const unsigned sx = (unsigned)a.nzp, sy = (unsigned)a.qsy;
-                const unsigned kfold = (unsigned)AX_MAGIC_I * (sy + sx + 1u);
+                const char *__restrict__ q0 = a.quad0;
+                const char *__restrict__ q1 = a.quad1;
+                const float sx = a.nxq_f;
+                const int sy = a.qshift;
+                const unsigned kb = ((unsigned)AX_MAGIC_I << sy) + ((unsigned)AX_MAGIC_I << 4);
                 const float2 dxy = make_float2(fdx, fdy);
                 int j = j0;
                 // head: up to the next multiple of four
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
                     const float2 e = k == 1 ? exy[1] : k == 2 ? exy[2] : exy[3];
                     const float z = k == 1 ? ezk[1] : k == 2 ? ezk[2] : ezk[3];
                     ax_sample_quad<NCH>(q0, q1, __ffma2_rn(make_float2(fb, fb), dxy, e), fmaf(fb, fdz, z), sx, sy,
-                                        kfold, s0, s1);
+                                        kb, s0, s1);
                 }
                 float fm = (float)j;
 #pragma unroll 1
@@ -228,14 +236,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ax_sample_quad<NCH>(q0, q1, __ffma2_rn(fm2, dxy, exy[k]), fmaf(fm, fdz, ezk[k]), sx,
-                                            sy, kfold, s0, s1);
+                                            sy, kb, s0, s1);
                     fm += 4.f;
                 }
                 for (int k = 0; j < ns; ++j, ++k) {
                     const float2 e = k == 0 ? exy[0] : k == 1 ? exy[1] : exy[2];
                     const float z = k == 0 ? ezk[0] : k == 1 ? ezk[1] : ezk[2];
                     ax_sample_quad<NCH>(q0, q1, __ffma2_rn(make_float2(fm, fm), dxy, e), fmaf(fm, fdz, z), sx, sy,
-                                        kfold, s0, s1);
+                                        kb, s0, s1);
                 }
             } else {
                 const float *__restrict__ v0 = a.vol0;
@@ -306,9 +314,10 @@ static void launch_ax(const AxArgs &a, int count, cudaStream_t st)
     }
 }
 
-// resident layout -> quad-packed copy (one float4 per cell corner (y,x) and depth z)
+// resident layout -> quad-packed copy (one float4 per cell corner (y,x) and depth z; columns
+// padded to zq = 2^k entries so that the march needs no integer multiply)
 __global__ void __launch_bounds__(256) k_quad_pack(const float *__restrict__ P, float4 *__restrict__ Q,
-                                                   int nyq, int nxq, int nxp, int nzp)
+                                                   int nyq, int nxq, int nxp, int nzp, int zq)
 {
     const size_t n = (size_t)nyq * nxq * nzp;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
@@ -318,14 +327,23 @@ __global__ void __launch_bounds__(256) k_quad_pack(const float *__restrict__ P, 
         const int x = (int)(c % nxq), y = (int)(c / nxq);
         const float *p = P + ((size_t)y * nxp + x) * nzp + z;
         const size_t sy = (size_t)nxp * nzp;
-        Q[t] = make_float4(__ldg(p), __ldg(p + nzp), __ldg(p + sy), __ldg(p + sy + nzp));
+        Q[c * zq + z] = make_float4(__ldg(p), __ldg(p + nzp), __ldg(p + sy), __ldg(p + sy + nzp));
     }
+}
+
+static int quad_zq(const PaxPlan *p)
+{
+    int zq = 8;
+    while (zq < p->nzp) zq <<= 1;
+    return zq;
 }
 
 extern "C" size_t pax_ax_workspace_bytes(const PaxPlan *p, int n_channels)
 {
     if (!p || n_channels < 1) return 0;
-    return (size_t)n_channels * (size_t)(p->nyp - 1) * (p->nxp - 1) * p->nzp * sizeof(float4);
+    if ((size_t)(p->nyp - 1) * (p->nxp - 1) >= ((size_t)1 << 23)) return 0;   // column index must fit a mantissa
+    if ((size_t)(p->nyp - 1) * (p->nxp - 1) * quad_zq(p) * sizeof(float4) >= ((size_t)1 << 32)) return 0;
+    return (size_t)n_channels * (size_t)(p->nyp - 1) * (p->nxp - 1) * quad_zq(p) * sizeof(float4);
 }
 
 extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_res1, int first,
@@ -355,14 +373,20 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
     cudaStream_t st = (cudaStream_t)stream;
     if (workspace) {
         PAX_REQUIRE(((uintptr_t)workspace & 15) == 0, "pax_ax: workspace must be 16-byte aligned");
-        const int nyq = p->nyp - 1, nxq = p->nxp - 1;
-        const size_t per = (size_t)nyq * nxq * p->nzp;
-        PAX_REQUIRE(per + 1 < ((size_t)1 << 32), "pax_ax: quad volume exceeds 2^32 entries");
+        const int nyq = p->nyp - 1, nxq = p->nxp - 1, zq = quad_zq(p);
+        PAX_REQUIRE((size_t)nyq * nxq < ((size_t)1 << 23),
+                    "pax_ax: in-plane size too large for the workspace kernel; pass workspace=NULL");
+        const size_t per = (size_t)nyq * nxq * zq;
         float4 *q = reinterpret_cast<float4 *>(workspace);
         const int blocks = 148 * 16;
-        k_quad_pack<<<blocks, 256, 0, st>>>(vol_res0, q, nyq, nxq, p->nxp, p->nzp);
-        if (vol_res1) k_quad_pack<<<blocks, 256, 0, st>>>(vol_res1, q + per, nyq, nxq, p->nxp, p->nzp);
-        a.quad0 = q; a.quad1 = vol_res1 ? q + per : nullptr; a.qsy = nxq * p->nzp;
+        k_quad_pack<<<blocks, 256, 0, st>>>(vol_res0, q, nyq, nxq, p->nxp, p->nzp, zq);
+        if (vol_res1) k_quad_pack<<<blocks, 256, 0, st>>>(vol_res1, q + per, nyq, nxq, p->nxp, p->nzp, zq);
+        int qshift = 4;
+        while ((1 << (qshift - 4)) < zq) ++qshift;
+        PAX_REQUIRE(per * sizeof(float4) < ((size_t)1 << 32), "pax_ax: quad channel exceeds 4 GB; pass workspace=NULL");
+        a.quad0 = reinterpret_cast<const char *>(q);
+        a.quad1 = vol_res1 ? reinterpret_cast<const char *>(q + per) : nullptr;
+        a.qshift = qshift; a.nxq_f = (float)nxq;
         if (epi->mode == PAX_AX_RESIDUAL) {
             const char *ev = getenv("PAX_AX_VARIANT");      // tuning hook (tools/profile_step.py)
             switch (ev ? atoi(ev) : 0) {
@@ -379,7 +403,7 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
         } else if (vol_res1) launch_ax<2, PAX_AX_PLAIN, true>(a, count, st);
         else launch_ax<1, PAX_AX_PLAIN, true>(a, count, st);
     } else {
-        a.quad0 = a.quad1 = nullptr; a.qsy = 0;
+        a.quad0 = a.quad1 = nullptr; a.qshift = 0; a.nxq_f = 0.f;
         if (epi->mode == PAX_AX_RESIDUAL) launch_ax<1, PAX_AX_RESIDUAL, false>(a, count, st);
         else if (vol_res1) launch_ax<2, PAX_AX_PLAIN, false>(a, count, st);
         else launch_ax<1, PAX_AX_PLAIN, false>(a, count, st);

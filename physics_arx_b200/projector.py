@@ -107,6 +107,8 @@ class Plan:
         if not self.use_workspace:
             return None
         need = int(self.lib.pax_ax_workspace_bytes(self._h, channels))
+        if need == 0:                  # geometry outside the workspace kernel's range
+            return None
         if self._work is None or self._work.numel() * 4 < need:
             self._work = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
         return self._work

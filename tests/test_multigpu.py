@@ -1,0 +1,69 @@
+"""N-GPU angle-sharded run vs the 1-GPU run on the same inputs: the only
+difference allowed is the summation order of the all-reduce.  Needs >= 2 GPUs (gpurun --gpus 2);
+skipped otherwise."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from physics_arx_b200.phantom import artifact_volume, lung_phantom, make_geometry
+    from physics_arx_b200.pipeline import SCBCTPipeline
+    geo = make_geometry((16, 40, 40), (10.0, 6.0, 6.0), (40, 72), (6.0, 4.0), off_detector=(0.0, -30.0))
+    angles = np.linspace(0, 2 * np.pi, 23)
+    ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    art = artifact_volume(geo.nVoxel, seed=1)
+    kw = dict(niter=3, blocksize=5, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=3)
+    sharded = SCBCTPipeline(geo, angles, group=dist.group.WORLD, **kw).run_host(ct, art).numpy().copy()
+    ok, info = True, ""
+    if rank == 0:
+        single = SCBCTPipeline(geo, angles, **kw).run_host(ct, art).numpy()
+        hu = np.abs(sharded - single) * 4095.0
+        ok = bool(hu.mean() <= 0.05 and hu.max() <= 0.5)
+        info = f"mean {hu.mean():.2e} HU max {hu.max():.2e} HU"
+    # every rank must hold the same volume
+    t = torch.from_numpy(sharded).cuda()
+    ref = t.clone()
+    dist.broadcast(ref, src=0)
+    ok &= bool(torch.equal(t, ref))
+    q.put((rank, ok, info))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_pipeline_equals_single_gpu():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
