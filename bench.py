@@ -39,7 +39,7 @@ def get_config(name):
     return cfg
 
 
-def describe(cfg, n_gpus):
+def describe(cfg, n_gpus, shard="angles"):
     geo = cfg["geo"]
     nsub = -(-len(cfg["angles"]) // cfg["blocksize"])
     return {
@@ -49,8 +49,10 @@ def describe(cfg, n_gpus):
                     f"{cfg['niter']}-iteration OS-SART (blocksize {cfg['blocksize']}, {nsub} subsets)",
         "niter": cfg["niter"], "blocksize": cfg["blocksize"], "I0": cfg["I0"], "sigma": cfg["sigma"],
         "accuracy": float(geo.accuracy),
-        "parallelism": "1 GPU" if n_gpus == 1 else
-                       f"angles of each subset interleaved over {n_gpus} GPUs, NCCL all-reduce of the update per subset",
+        "parallelism": "1 GPU" if n_gpus == 1 else (
+            f"angles of each subset interleaved over {n_gpus} GPUs" if shard == "angles" else
+            f"every angle of each subset, detector rows split in {n_gpus} bands (one per GPU; subsets of 20 "
+            f"do not divide by {n_gpus})") + ", volume replicated, NCCL all-reduce of the partial update per subset",
         "l2": "per-step working set (projections + volumes, ~2.4 GB at C2) exceeds the 126 MB L2; no flush",
     }
 
@@ -162,6 +164,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard", default="auto", choices=["auto", "angles", "rows"],
+                    help="how a subset's rays are cut over the ranks (physics_arx_b200/dist.py)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +203,7 @@ def main():
     out_host = torch.empty(ct_host.shape, dtype=torch.float32).pin_memory()
     ct_dev, art_dev = ct_host.cuda(), art_host.cuda()
     pipe = SCBCTPipeline(geo, angles, niter=cfg["niter"], blocksize=cfg["blocksize"], I0=cfg["I0"],
-                         sigma=cfg["sigma"], scatter_scale=SCATTER_SCALE, seed=0, group=group)
+                         sigma=cfg["sigma"], scatter_scale=SCATTER_SCALE, seed=0, group=group, shard=args.shard)
 
     def barrier():
         torch.cuda.synchronize()
@@ -290,7 +294,7 @@ def main():
             "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": describe(cfg, world),
+            "data": "synthetic", "config": describe(cfg, world, pipe.st.shard),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "k_ax<1,RESIDUAL,32>",
                          "peak_source": peak_src, "avg_launch_ms": avg_ms,

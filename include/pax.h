@@ -137,11 +137,13 @@ int pax_reduce_max(const float *x, size_t n, float *out_dev, void *stream);
 /* turn the order-encoded running max of PaxAxEpilogue.maxout into a float, in place */
 int pax_max_decode(uint32_t *word_dev, void *stream);
 
-/* tigre.utilities.CTnoise.add -- reference :88.  In place on n floats whose global
- * element index starts at index0 (noise is a function of (seed, global index) only, so
- * it does not depend on how projections are sharded).  *max_dev = max(proj). */
-int pax_ctnoise(float *proj, size_t n, uint64_t index0, double I0, double mean, double std,
-                const float *max_dev, uint64_t seed, void *stream);
+/* tigre.utilities.CTnoise.add -- reference :88.  In place on n floats.  Noise is a function of
+ * (seed, global element index) only, so it does not depend on how projections are sharded:
+ * local element e has global index  index0 + (e / inner) * outer_stride + (e % inner)
+ * (an [n/inner][inner] block cut out of the global array; inner = 0 means contiguous).
+ * *max_dev = max(proj) over the WHOLE projection set. */
+int pax_ctnoise(float *proj, size_t n, uint64_t index0, size_t inner, uint64_t outer_stride, double I0,
+                double mean, double std, const float *max_dev, uint64_t seed, void *stream);
 
 #ifdef __cplusplus
 }

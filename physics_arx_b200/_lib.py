@@ -60,8 +60,9 @@ SYMBOLS = [
                                      ctypes.c_float, ctypes.c_float, _VP, _VP]),
     ("pax_compute_v", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_double, _VP, _VP]),
     ("pax_reduce_max", ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP]),
-    ("pax_ctnoise", ctypes.c_int, [_VP, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_double,
-                                   ctypes.c_double, ctypes.c_double, _VP, ctypes.c_uint64, _VP]),
+    ("pax_ctnoise", ctypes.c_int, [_VP, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_uint64,
+                                   ctypes.c_double, ctypes.c_double, ctypes.c_double, _VP, ctypes.c_uint64,
+                                   _VP]),
 ]
 
 _lib = None

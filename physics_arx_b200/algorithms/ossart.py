@@ -21,7 +21,7 @@ import torch
 from .. import _lib
 from ..geometry import order_subsets
 from ..projector import Plan, _device_from_gpuids, _to_cuda
-from ..dist import shard_blocks, subset_geometry
+from ..dist import choose_shard, row_window_geometry, shard_blocks, shard_rows, subset_geometry
 
 
 def _dist_info(group, distributed):
@@ -38,7 +38,7 @@ class OSSARTState:
     """Set-up products of one OS-SART problem (the role of TIGRE's IterativeReconAlg)."""
 
     def __init__(self, proj, geo, angles, blocksize=20, OrderStrategy=None, w_variant="matlab",
-                 v_variant="A", group=None, distributed=None, device=None, seed=0):
+                 v_variant="A", group=None, distributed=None, device=None, seed=0, shard="auto"):
         import torch.distributed as dist
         angles = np.asarray(angles, dtype=np.float64)
         if angles.ndim == 2:
@@ -49,17 +49,35 @@ class OSSARTState:
         self.geo, self.n = geo, n
         self.w_variant = w_variant
         self.blocks = order_subsets(n, blocksize, OrderStrategy, seed)
-        local, self.ranges = shard_blocks(self.blocks, self.rank, self.world)
-        self.local_idx = local
         dev = proj.device if proj is not None else torch.device(
             "cuda", torch.cuda.current_device() if device is None else int(device))
-        # a rank may own no angle at all (n < world): keep one dummy angle so a plan exists
-        plan_idx = local if len(local) else np.array([0])
-        self.plan = Plan(subset_geometry(geo, plan_idx, n), angles[plan_idx], device=dev.index)
+        nv_full, nu = (int(v) for v in geo.nDetector)
+        self.shard = choose_shard(self.blocks, self.world, shard) if self.world > 1 else "angles"
+        if self.shard == "rows":
+            # every angle, a band of detector rows: the band is a detector of its own
+            self.v0, self.v1 = shard_rows(nv_full, self.rank, self.world)
+            local, self.ranges = shard_blocks(self.blocks, 0, 1)
+            empty = self.v1 <= self.v0
+            band = (0, 1) if empty else (self.v0, self.v1)      # keep a 1-row plan on an idle rank
+            plan_geo, plan_idx = row_window_geometry(geo, *band), local
+            if empty:
+                self.ranges = [(f, 0) for f, _ in self.ranges]
+        else:
+            self.v0, self.v1 = 0, nv_full
+            local, self.ranges = shard_blocks(self.blocks, self.rank, self.world)
+            # a rank may own no angle at all (n < world): keep one dummy angle so a plan exists
+            plan_idx = local if len(local) else np.array([0])
+            plan_geo = subset_geometry(geo, plan_idx, n)
+        self.local_idx = local
+        self.plan = Plan(plan_geo, angles[plan_idx], device=dev.index)
+        self.plan.w_geo = geo
+        n_own = len(local) if (self.shard == "angles" or self.v1 > self.v0) else 0
+        rows = self.v1 - self.v0 if self.shard == "rows" else nv_full
         if proj is None:                                    # caller fills the rank-local buffer
-            nv, nu = (int(v) for v in geo.nDetector)
-            self.b = torch.empty((max(len(local), 1), nv, nu), dtype=torch.float32,
-                                 device=dev)[:len(local)]
+            self.b = torch.empty((max(n_own, 1), max(rows, 1), nu), dtype=torch.float32,
+                                 device=dev)[:n_own]
+        elif self.shard == "rows":
+            self.b = proj[:, self.v0:self.v1, :].contiguous()
         elif len(local) == n and np.array_equal(local, np.arange(n)):
             self.b = proj                                   # ordered, single rank: no copy
         else:
@@ -145,7 +163,7 @@ def ossart(proj, geo, angles, niter, **kwargs):
 
     kwargs: blocksize=20, lmbda=1, lmbda_red=0.99, OrderStrategy=None, init=None,
     noneg=True, verbose=False, computel2=False, gpuids=None; build extras: w_variant,
-    v_variant, group / distributed (angle sharding over a torch.distributed group).
+    v_variant, group / distributed / shard (sharding over a torch.distributed group; dist.py).
     Returns the (Z,Y,X) float32 volume (NumPy in -> NumPy out); with computel2 also the
     per-iteration ||b - Ax||_2.
     """
@@ -160,7 +178,8 @@ def ossart(proj, geo, angles, niter, **kwargs):
     gpuids = kwargs.pop("gpuids", None)
     if kwargs.pop("Quameasopts", None) is not None:
         raise NotImplementedError("Quameasopts is not on this path (commented out in the reference, :103)")
-    state_kw = {k: kwargs.pop(k) for k in ("w_variant", "v_variant", "group", "distributed") if k in kwargs}
+    state_kw = {k: kwargs.pop(k) for k in ("w_variant", "v_variant", "group", "distributed", "shard")
+                if k in kwargs}
     if kwargs:
         raise TypeError(f"ossart: unexpected keyword arguments {sorted(kwargs)}")
     if not torch.cuda.is_available():

@@ -307,13 +307,15 @@ __device__ __forceinline__ void philox4x32_10(unsigned c[4], unsigned k0, unsign
 
 // CTnoise.add (reference :88) in double: I0 = 1e8 counts do not fit fp32.
 __global__ void __launch_bounds__(256) k_ctnoise(float *__restrict__ p, size_t n, uint64_t index0,
-                                                 double I0, double mean, double sd,
+                                                 size_t inner, uint64_t outer_stride, double I0,
+                                                 double mean, double sd,
                                                  const float *__restrict__ max_dev, uint64_t seed)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const double m = (double)*max_dev;
-    const uint64_t idx = index0 + e;
+    // local element e = (outer, in) of an [n/inner][inner] block cut out of the global array
+    const uint64_t idx = index0 + (e / inner) * outer_stride + (e % inner);
     unsigned c[4] = {(unsigned)idx, (unsigned)(idx >> 32), 0u, 0u};
     philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
     const double inv32 = 1.0 / 4294967296.0;
@@ -336,13 +338,16 @@ __global__ void __launch_bounds__(256) k_ctnoise(float *__restrict__ p, size_t n
     p[e] = (float)(-log(I / I0) * m);
 }
 
-extern "C" int pax_ctnoise(float *proj, size_t n, uint64_t index0, double I0, double mean, double sd,
-                           const float *max_dev, uint64_t seed, void *stream)
+extern "C" int pax_ctnoise(float *proj, size_t n, uint64_t index0, size_t inner, uint64_t outer_stride,
+                           double I0, double mean, double sd, const float *max_dev, uint64_t seed,
+                           void *stream)
 {
     PAX_REQUIRE(proj && max_dev && n > 0, "pax_ctnoise: bad argument");
     PAX_REQUIRE(I0 > 0 && sd >= 0, "pax_ctnoise: need I0 > 0 and std >= 0");
-    k_ctnoise<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(proj, n, index0, I0, mean,
-                                                                             sd, max_dev, seed);
+    if (inner == 0) { inner = n; outer_stride = n; }
+    PAX_REQUIRE(n % inner == 0 && outer_stride >= inner, "pax_ctnoise: bad block shape");
+    k_ctnoise<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        proj, n, index0, inner, outer_stride, I0, mean, sd, max_dev, seed);
     PAX_CHECK_CUDA(cudaGetLastError());
     return PAX_OK;
 }

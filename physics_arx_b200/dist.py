@@ -1,5 +1,14 @@
-"""Angle sharding for multi-GPU runs: one process per GPU, the angles of
-every OS-SART subset interleaved over the ranks, volume replicated.  Host logic only."""
+"""Sharding for multi-GPU runs: one process per GPU, volume replicated, one
+all-reduce of the partial volume update per OS-SART subset.  Host logic only.
+
+Two ways to cut a subset's rays over the ranks, both linear in the projections so the partial
+updates (and the partial V maps) add up exactly:
+  'angles'  the prescribed scheme: the angles of every subset interleaved over the ranks;
+  'rows'    every rank takes ALL angles of the subset but only a band of detector rows.  A row
+            band of a detector is itself a (shorter, V-shifted) detector, so nothing below the
+            geometry bag changes; bilinear interpolation across a band boundary splits into two
+            ramps that sum to one.  Balanced for any rank count (20 angles over 8 ranks are not).
+  'auto'    'angles' when every subset divides evenly, else 'rows'."""
 from __future__ import annotations
 
 import numpy as np
@@ -37,3 +46,40 @@ def subset_geometry(geo, idx, n):
         if (width == 1 and arr.shape == (n,)) or (width > 1 and arr.shape == (n, width)):
             setattr(gs, name, arr[idx])
     return gs
+
+
+def shard_rows(n_rows, rank, world, align=32):
+    """Row band [v0, v1) of rank `rank`: contiguous, aligned to `align` rows where possible."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    units = -(-n_rows // align)
+    if units >= world:
+        lo = (units * rank) // world * align
+        hi = (units * (rank + 1)) // world * align
+    else:                                   # fewer aligned bands than ranks: split single rows
+        lo = (n_rows * rank) // world
+        hi = (n_rows * (rank + 1)) // world
+    return min(lo, n_rows), min(hi, n_rows)
+
+
+def row_window_geometry(geo, v0, v1, n_angles=None):
+    """The detector rows [v0, v1) of `geo` as a geometry of their own (A.2: a pixel's v coordinate
+    is (v - nV/2 + 1/2) dV + offV, so the band is a detector of v1-v0 rows shifted in V)."""
+    gs = geo.copy()
+    nv = int(np.asarray(geo.nDetector)[0])
+    dv = float(np.asarray(geo.dDetector, dtype=np.float64)[0])
+    shift = (0.5 * (v0 + v1) - 0.5 * nv) * dv
+    gs.nDetector = np.array((v1 - v0, int(np.asarray(geo.nDetector)[1])))
+    gs.sDetector = gs.nDetector * np.asarray(geo.dDetector, dtype=np.float64)
+    off = np.array(np.asarray(geo.offDetector, dtype=np.float64), copy=True)
+    off[..., 0] += shift
+    gs.offDetector = off
+    return gs
+
+
+def choose_shard(blocks, world, shard="auto"):
+    if shard in ("angles", "rows"):
+        return shard
+    if shard != "auto":
+        raise ValueError(f"unknown shard mode {shard!r}")
+    return "angles" if all(len(b) % world == 0 for b in blocks) else "rows"

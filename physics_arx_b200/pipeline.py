@@ -25,7 +25,7 @@ from .projector import _ptr, _stream
 class SCBCTPipeline:
     def __init__(self, geo, angles, niter=20, blocksize=20, I0=1e8, sigma=4.0, scatter_scale=1.0,
                  lmbda=1.0, lmbda_red=0.99, seed=0, group=None, device=None, w_variant="matlab",
-                 v_variant="A"):
+                 v_variant="A", shard="auto"):
         if not torch.cuda.is_available():
             raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
@@ -40,10 +40,10 @@ class SCBCTPipeline:
         with torch.cuda.device(self.device):
             self.st = OSSARTState(None, geo, self.angles, blocksize, None, w_variant=w_variant,
                                   v_variant=v_variant, group=group, distributed=group is not None,
-                                  device=self.device.index)
+                                  device=self.device.index, shard=shard)
         st = self.st
         self.plan = st.plan
-        self.n_local = len(st.local_idx)
+        self.n_local = int(st.b.shape[0])
         self.local_idx = st.local_idx
         p = self.plan
         self.ct_res = p.new_volume()
@@ -76,18 +76,27 @@ class SCBCTPipeline:
         if self.group is not None:
             dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
         # noise is keyed by the GLOBAL pixel index, so the result does not depend on the sharding
-        npix = p.nv * p.nu
+        nu = p.nu
+        nv_full = int(np.asarray(self.geo.nDetector)[0])
+        npix = nv_full * nu
         lib = p.lib
-        runs = _contiguous_runs(self.local_idx)
-        pos = 0
         with torch.cuda.device(self.device):
-            for g0, cnt in runs:
-                view = st.b[pos:pos + cnt]
-                _lib.check(lib.pax_ctnoise(_ptr(view), view.numel(), ctypes.c_uint64(int(g0) * npix),
-                                           self.I0, 0.0, self.sigma, _ptr(m),
-                                           ctypes.c_uint64(self.seed), _stream()), "pax_ctnoise")
-                self.launches += 1
-                pos += cnt
+            if st.shard == "rows":          # (N, rows, U) band of every angle
+                if self.n_local:
+                    _lib.check(lib.pax_ctnoise(_ptr(st.b), st.b.numel(), ctypes.c_uint64(st.v0 * nu),
+                                               (st.v1 - st.v0) * nu, ctypes.c_uint64(npix), self.I0, 0.0,
+                                               self.sigma, _ptr(m), ctypes.c_uint64(self.seed), _stream()),
+                               "pax_ctnoise")
+                    self.launches += 1
+            else:                           # whole projections of this rank's angles
+                pos = 0
+                for g0, cnt in _contiguous_runs(self.local_idx):
+                    view = st.b[pos:pos + cnt]
+                    _lib.check(lib.pax_ctnoise(_ptr(view), view.numel(), ctypes.c_uint64(int(g0) * npix), 0,
+                                               0, self.I0, 0.0, self.sigma, _ptr(m),
+                                               ctypes.c_uint64(self.seed), _stream()), "pax_ctnoise")
+                    self.launches += 1
+                    pos += cnt
         return st.b
 
     def reconstruct(self):

@@ -54,6 +54,8 @@ class Plan:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         g, rows = geo.pack(angles)
         self.geo = geo
+        self.w_geo = geo               # geometry the W box is derived from (the FULL detector when
+                                       # this plan describes a row band of it)
         self.n_angles = rows.shape[0]
         self.nz, self.ny, self.nx = int(g[0]), int(g[1]), int(g[2])
         self.nv, self.nu = int(g[3]), int(g[4])
@@ -115,7 +117,7 @@ class Plan:
 
     # --------------------------------------------------------------- projectors
     def _w_box(self, w_variant):
-        (hz, hy, hx), thr = self.geo.w_box(w_variant)
+        (hz, hy, hx), thr = self.w_geo.w_box(w_variant)
         return float(hz), float(hy), float(hx), float(thr)
 
     def axpy(self, y_res, x_res, a):

@@ -41,7 +41,7 @@ def add(projections, Poisson=1e5, Gaussian=np.array([0, 0.5]), seed=0, index0=0,
         import torch.distributed as dist
         dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
     with torch.cuda.device(p.device):
-        _lib.check(lib.pax_ctnoise(_ptr(p), p.numel(), ctypes.c_uint64(int(index0)), float(Poisson),
+        _lib.check(lib.pax_ctnoise(_ptr(p), p.numel(), ctypes.c_uint64(int(index0)), 0, 0, float(Poisson),
                                    float(Gaussian[0]), float(Gaussian[1]), _ptr(m),
                                    ctypes.c_uint64(int(seed)), _stream()), "pax_ctnoise")
     return p.cpu().numpy() if was_np else p

@@ -173,3 +173,54 @@ def test_phantoms_are_seeded_and_in_range():
     art = artifact_volume((16, 32, 32), seed=1)
     assert abs(art.mean()) < 1e-3 and np.abs(art).max() <= 0.0501
     assert len(c["angles"]) == 256 and c["niter"] == 5
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8, 40])
+def test_shard_rows_partitions_the_detector(world):
+    from physics_arx_b200.dist import shard_rows
+    for nv in (768, 256, 100, 33, 7):
+        bands = [shard_rows(nv, r, world) for r in range(world)]
+        assert bands[0][0] == 0 and bands[-1][1] == nv
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        assert all(v1 >= v0 for v0, v1 in bands)
+    assert shard_rows(768, 3, 8) == (288, 384)
+
+
+def test_choose_shard_auto():
+    from physics_arx_b200 import order_subsets
+    from physics_arx_b200.dist import choose_shard
+    blocks = order_subsets(656, 20)                      # 32 x 20 + 16
+    assert choose_shard(blocks, 2) == "angles" and choose_shard(blocks, 4) == "angles"
+    assert choose_shard(blocks, 8) == "rows"
+    assert choose_shard(blocks, 8, "angles") == "angles"
+    with pytest.raises(ValueError):
+        choose_shard(blocks, 2, "columns")
+
+
+def test_row_band_is_a_detector_of_its_own(oracle):
+    """Ax of a band == rows of the full Ax; Atb / V over the bands sum to the full Atb / V."""
+    from conftest import rel_l2
+    from physics_arx_b200.dist import row_window_geometry, shard_rows
+    from physics_arx_b200.phantom import make_geometry
+    geo = make_geometry((8, 16, 16), (14.0, 9.0, 9.0), (22, 30), (8.0, 7.0), off_detector=(3.0, -25.0))
+    ang = np.array([0.2, 1.9, 3.3, 5.0])
+    rng = np.random.default_rng(3)
+    vol = rng.random((8, 16, 16))
+    proj = rng.standard_normal((4, 22, 30))
+    full_ax, full_atb = oracle.ax(vol, geo, ang), oracle.atb(proj, geo, ang)
+    full_v = oracle.atb(None, geo, ang, vscale=geo.v_scale())
+    full_w = oracle.compute_w(geo, ang)
+    acc, vacc = 0.0, 0.0
+    for r in range(3):
+        v0, v1 = shard_rows(22, r, 3, align=4)
+        gb = row_window_geometry(geo, v0, v1)
+        assert rel_l2(oracle.ax(vol, gb, ang), full_ax[:, v0:v1]) < 1e-12
+        acc = acc + oracle.atb(proj[:, v0:v1], gb, ang)
+        vacc = vacc + oracle.atb(None, gb, ang, vscale=geo.v_scale())
+        # W must come from the FULL geometry's box (its z size depends on sDetector)
+        (hz, hy, hx), thr = geo.w_box("matlab")
+        gb_w = gb.copy()
+        assert gb.w_box("matlab")[0][0] != hz or v1 - v0 == 22
+    assert rel_l2(acc, full_atb) < 1e-12
+    assert rel_l2(vacc, full_v) < 1e-12
+    assert full_w.shape == (4, 22, 30)

@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, shard):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -32,7 +32,9 @@ def _worker(rank, world, port, q):
     ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
     art = artifact_volume(geo.nVoxel, seed=1)
     kw = dict(niter=3, blocksize=5, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=3)
-    sharded = SCBCTPipeline(geo, angles, group=dist.group.WORLD, **kw).run_host(ct, art).numpy().copy()
+    pipe = SCBCTPipeline(geo, angles, group=dist.group.WORLD, shard=shard, **kw)
+    assert pipe.st.shard == shard
+    sharded = pipe.run_host(ct, art).numpy().copy()
     ok, info = True, ""
     if rank == 0:
         single = SCBCTPipeline(geo, angles, **kw).run_host(ct, art).numpy()
@@ -50,7 +52,8 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-def test_sharded_pipeline_equals_single_gpu():
+@pytest.mark.parametrize("shard", ["angles", "rows"])
+def test_sharded_pipeline_equals_single_gpu(shard):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -60,7 +63,7 @@ def test_sharded_pipeline_equals_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, shard)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
