@@ -70,6 +70,9 @@ typedef struct PaxAxEpilogue {
     float w_thr;                    /* chord lengths <= w_thr give W = 0 */
     double *sumsq;                  /* optional device scalar: += sum (b-P0)^2 (computel2) */
     unsigned long long *nsamples;   /* optional device scalar: += trilinear samples taken */
+    float *out1;                    /* optional (PLAIN, two channels): P1 goes here, (count,V,U), and
+                                       out = a0*P0 + c*L -- both line integrals from ONE pass, to fan
+                                       several scatter scales out of it afterwards (pax_lincomb) */
     uint32_t *maxout;               /* optional device word (PLAIN): running max of out, order-encoded;
                                        zero it first, finish with pax_max_decode -- the normalising
                                        max of CTnoise.add fused into the projection epilogue */
@@ -131,6 +134,10 @@ int pax_compute_w(const PaxPlan *plan, int first, int count, float half_z, float
                   float half_x, float thr, float *w_out, void *stream);
 int pax_compute_v(const PaxPlan *plan, int first, int count, double vscale, float *v_out,
                   void *stream);
+
+/* out = a*x + b*y over n floats (out may alias x or y): the projection-domain scatter combine
+ * P = P_ct + s*P_art for one variation of a batch */
+int pax_lincomb(float *out, const float *x, const float *y, float a, float b, size_t n, void *stream);
 
 /* max over n floats -> *out_dev (device float) */
 int pax_reduce_max(const float *x, size_t n, float *out_dev, void *stream);

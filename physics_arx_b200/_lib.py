@@ -28,7 +28,7 @@ class PaxAxEpilogue(ctypes.Structure):
                 ("c", ctypes.c_float), ("b", ctypes.c_void_p),
                 ("w_half_z", ctypes.c_float), ("w_half_y", ctypes.c_float), ("w_half_x", ctypes.c_float),
                 ("w_thr", ctypes.c_float), ("sumsq", ctypes.c_void_p), ("nsamples", ctypes.c_void_p),
-                ("maxout", ctypes.c_void_p)]
+                ("out1", ctypes.c_void_p), ("maxout", ctypes.c_void_p)]
 
 
 class PaxAtbEpilogue(ctypes.Structure):
@@ -50,6 +50,7 @@ SYMBOLS = [
     ("pax_vol_unpack", ctypes.c_int, [_VP, _VP, _VP, _VP]),
     ("pax_vol_axpy", ctypes.c_int, [_VP, _VP, _VP, ctypes.c_float, _VP]),
     ("pax_max_decode", ctypes.c_int, [_VP, _VP]),
+    ("pax_lincomb", ctypes.c_int, [_VP, _VP, _VP, ctypes.c_float, ctypes.c_float, ctypes.c_size_t, _VP]),
     ("pax_ax_workspace_bytes", ctypes.c_size_t, [_VP, ctypes.c_int]),
     ("pax_ax", ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
                               ctypes.POINTER(PaxAxEpilogue), _VP, _VP]),

@@ -36,6 +36,7 @@ struct AxArgs {
     int qshift;                   // log2 of the quad column stride in bytes
     float nxq_f;                  // quad columns per y row
     float *out;
+    float *out1;
     const float *b;
     double *sumsq;
     unsigned long long *nsamples;
@@ -271,7 +272,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_ax(const AxArgs a)
         const float p0 = s0 * steplen;
         if (MODE == PAX_AX_PLAIN) {
             float val = a.a0 * p0;
-            if (NCH == 2) val = fmaf(a.a1, s1 * steplen, val);
+            if (NCH == 2) {
+                if (a.out1) a.out1[o] = s1 * steplen;
+                else val = fmaf(a.a1, s1 * steplen, val);
+            }
             if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
             a.out[o] = val;
             mymax = val;
@@ -358,9 +362,10 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
                 epi->mode);
     PAX_REQUIRE(epi->mode != PAX_AX_RESIDUAL || epi->b, "pax_ax: residual mode needs b");
     PAX_REQUIRE(epi->mode != PAX_AX_RESIDUAL || !vol_res1, "pax_ax: residual mode is single-channel");
+    PAX_REQUIRE(!epi->out1 || (vol_res1 && epi->mode == PAX_AX_PLAIN), "pax_ax: out1 needs two channels, PLAIN");
     AxArgs a;
     a.angles = p->d_angles;
-    a.vol0 = vol_res0; a.vol1 = vol_res1; a.out = proj_out; a.b = epi->b;
+    a.vol0 = vol_res0; a.vol1 = vol_res1; a.out = proj_out; a.out1 = epi->out1; a.b = epi->b;
     a.sumsq = epi->sumsq; a.nsamples = epi->nsamples; a.maxout = epi->maxout;
     a.first = first; a.nv = p->geo.nDetecV; a.nu = p->geo.nDetecU;
     a.nxp = p->nxp; a.nzp = p->nzp;

@@ -278,6 +278,22 @@ __global__ void __launch_bounds__(256) k_axpy(float4 *__restrict__ y, const floa
     }
 }
 
+__global__ void __launch_bounds__(256) k_lincomb(float *out, const float *x, const float *y, float a,
+                                                 float b, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = fmaf(a, x[i], b * y[i]);
+}
+
+extern "C" int pax_lincomb(float *out, const float *x, const float *y, float a, float b, size_t n,
+                           void *stream)
+{
+    PAX_REQUIRE(out && x && y && n > 0, "pax_lincomb: bad argument");
+    k_lincomb<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(out, x, y, a, b, n);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
 // the rim of both operands is zero, so running over the whole padded array keeps it zero
 extern "C" int pax_vol_axpy(const PaxPlan *p, float *y_res, const float *x_res, float a, void *stream)
 {

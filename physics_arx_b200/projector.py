@@ -128,14 +128,18 @@ class Plan:
         return y_res
 
     def ax(self, res0, first=0, count=None, out=None, res1=None, a0=1.0, a1=0.0, c=0.0,
-           w_variant="matlab", nsamples=None, maxout=None):
-        """out[(count,V,U)] = a0*Ax(res0) + a1*Ax(res1) + c*chord.  (PAX_AX_PLAIN)"""
+           w_variant="matlab", nsamples=None, maxout=None, out1=None):
+        """out[(count,V,U)] = a0*Ax(res0) + a1*Ax(res1) + c*chord.  (PAX_AX_PLAIN)
+
+        With ``out1`` (and ``res1``) the second channel's line integrals go to ``out1`` instead of
+        being mixed in: both projections from one pass."""
         count = self.n_angles - first if count is None else count
         if out is None:
             out = torch.empty((count, self.nv, self.nu), dtype=torch.float32, device=self.device)
         hz, hy, hx, thr = self._w_box(w_variant)
         epi = _lib.PaxAxEpilogue(_lib.PAX_AX_PLAIN, a0, a1, c, None, hz, hy, hx, thr, None,
                                  nsamples.data_ptr() if nsamples is not None else None,
+                                 out1.data_ptr() if out1 is not None else None,
                                  maxout.data_ptr() if maxout is not None else None)
         if maxout is not None:
             maxout.zero_()
@@ -151,7 +155,7 @@ class Plan:
         """out = W * (b - Ax(res)) for angles [first, first+count).  (PAX_AX_RESIDUAL)"""
         hz, hy, hx, thr = self._w_box(w_variant)
         epi = _lib.PaxAxEpilogue(_lib.PAX_AX_RESIDUAL, 1.0, 0.0, 0.0, b.data_ptr(), hz, hy, hx, thr,
-                                 sumsq.data_ptr() if sumsq is not None else None, None, None)
+                                 sumsq.data_ptr() if sumsq is not None else None, None, None, None)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_ax(self._h, _ptr(res), None, first, count, _ptr(out),
                                        ctypes.byref(epi), _ptr(self._workspace(1)), _stream()), "pax_ax")
@@ -188,6 +192,16 @@ class Plan:
             _lib.check(self.lib.pax_compute_v(self._h, first, count, self.geo.v_scale(), _ptr(out),
                                               _stream()), "pax_compute_v")
         return out
+
+
+def lincomb(out, x, y, a, b):
+    """out = a*x + b*y on float32 CUDA tensors of equal size (libpax k_lincomb)."""
+    lib = _lib.load()
+    assert out.numel() == x.numel() == y.numel() and out.is_contiguous() and x.is_contiguous() and y.is_contiguous()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.pax_lincomb(_ptr(out), _ptr(x), _ptr(y), float(a), float(b), out.numel(), _stream()),
+                   "pax_lincomb")
+    return out
 
 
 def reduce_max(x):
