@@ -100,6 +100,22 @@ int pax_plan_create(const PaxGeo *geo, const double *angle_rows, int n_angles, P
 int pax_plan_destroy(PaxPlan *plan);
 int pax_plan_n_angles(const PaxPlan *plan);
 
+/* Which forward-projector kernel pax_ax runs.  Both evaluate the same sums on the same sample
+ * lattice (tigre.Ax 'interpolated') and agree to fp32 rounding:
+ *   RAY  one thread per ray, one trilinear gather per sample (csrc/ax.cu)
+ *   FAN  the rays of a detector column share their in-plane interpolation and are summed from
+ *        prefix tables (csrc/ax_fan.cu); pays off when the detector rows are finer than the slices
+ *   AUTO (default) FAN when the geometry makes the sharing worthwhile, else RAY.
+ * pax_plan_projector returns the kernel AUTO resolves to (or the forced one). */
+#define PAX_PROJECTOR_AUTO 0
+#define PAX_PROJECTOR_RAY 1
+#define PAX_PROJECTOR_FAN 2
+int pax_plan_set_projector(PaxPlan *plan, int kind);
+int pax_plan_projector(const PaxPlan *plan);
+/* tuning facts of the FAN kernel for this geometry: detector rows per CTA tile (0 = does not fit),
+ * warps per CTA, mean length in rows of the runs that share one lattice */
+int pax_plan_fan_info(const PaxPlan *plan, int *rows_per_tile, int *warps, double *mean_run);
+
 /* Resident volume layout ("z-column": (Y+2, X+2, Zp) floats, z fastest, zero rim).
  * pax_vol_elems = floats per channel.  pack/unpack convert from/to (Z,Y,X). */
 size_t pax_vol_elems(const PaxPlan *plan);
@@ -112,9 +128,10 @@ int pax_vol_axpy(const PaxPlan *plan, float *y_res, const float *x_res, float a,
 
 /* tigre.Ax(img, geo, angles, 'interpolated')  -- reference :86; angles [first, first+count)
  * of the plan; vol_res1 may be NULL (single channel). proj_out is (count,V,U).
- * workspace: device scratch of pax_ax_workspace_bytes(plan, channels) bytes, 16-byte aligned,
- * that receives the gather-friendly re-packing of the volume(s) for this call; NULL selects
- * the slower kernel that gathers from the resident layout directly. */
+ * workspace (RAY kernel only; pax_ax_workspace_bytes is 0 when the plan resolves to FAN): device
+ * scratch of pax_ax_workspace_bytes(plan, channels) bytes, 16-byte aligned, that receives the
+ * gather-friendly re-packing of the volume(s) for this call; NULL selects the slower ray kernel
+ * that gathers from the resident layout directly. */
 size_t pax_ax_workspace_bytes(const PaxPlan *plan, int n_channels);
 int pax_ax(const PaxPlan *plan, const float *vol_res0, const float *vol_res1, int first, int count,
            float *proj_out, const PaxAxEpilogue *epi, void *workspace, void *stream);

@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpax.so")
 
 PAX_AX_PLAIN, PAX_AX_RESIDUAL = 0, 1
 PAX_ATB_STORE, PAX_ATB_ADD, PAX_ATB_SART = 0, 1, 2
+PAX_PROJECTOR_AUTO, PAX_PROJECTOR_RAY, PAX_PROJECTOR_FAN = 0, 1, 2
 ANGLE_STRIDE = 8
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -45,6 +46,10 @@ SYMBOLS = [
                                        ctypes.POINTER(_VP)]),
     ("pax_plan_destroy", ctypes.c_int, [_VP]),
     ("pax_plan_n_angles", ctypes.c_int, [_VP]),
+    ("pax_plan_set_projector", ctypes.c_int, [_VP, ctypes.c_int]),
+    ("pax_plan_projector", ctypes.c_int, [_VP]),
+    ("pax_plan_fan_info", ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                         c_double_p]),
     ("pax_vol_elems", ctypes.c_size_t, [_VP]),
     ("pax_vol_pack", ctypes.c_int, [_VP, _VP, _VP, _VP]),
     ("pax_vol_unpack", ctypes.c_int, [_VP, _VP, _VP, _VP]),

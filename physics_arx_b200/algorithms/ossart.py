@@ -120,7 +120,7 @@ class OSSARTState:
             if ev is not None:
                 ev[1].record()
                 self.kernel_events.append((ev[0], ev[1], count))
-            self.launches += 2 if p.use_workspace else 1      # (quad re-pack +) projector
+            self.launches += p.ax_launches(1)                  # (quad re-pack +) projector
         if self.world == 1:
             p.atb(self.resid, first, count, x_res, _lib.PAX_ATB_SART, self.inv_v[s], lam, noneg)
             self.launches += 1

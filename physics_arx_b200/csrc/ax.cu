@@ -27,29 +27,6 @@
 
 #include "pax_internal.h"
 
-struct AxArgs {
-    const AngleDev *angles;
-    const float *vol0;
-    const float *vol1;
-    const char *quad0;            // quad-packed channels
-    const char *quad1;
-    int qshift;                   // log2 of the quad column stride in bytes
-    float nxq_f;                  // quad columns per y row
-    float *out;
-    float *out1;
-    const float *b;
-    double *sumsq;
-    unsigned long long *nsamples;
-    unsigned *maxout;
-    int first, nv, nu;
-    int nxp, nzp;                 // resident strides: x -> nzp, y -> nxp*nzp
-    float hix, hiy, hiz;          // exclusive upper bounds of valid padded coordinates
-    float loz;                    // inclusive lower z bound (PAX_ZOFF-1); x,y lower bound is 0
-    double acc;
-    float dX, dY, dZ;
-    float a0, a1, c;
-    float whx, why, whz, wthr;
-};
 
 #define AX_MAGIC 8388608.0f          // 2^23: (q + 2^23) rounded down keeps floor(q) in the mantissa
 #define AX_MAGIC_I 0x4B000000
@@ -345,6 +322,7 @@ static int quad_zq(const PaxPlan *p)
 extern "C" size_t pax_ax_workspace_bytes(const PaxPlan *p, int n_channels)
 {
     if (!p || n_channels < 1) return 0;
+    if (pax_plan_projector(p) == PAX_PROJECTOR_FAN) return 0;   // gathers from the resident layout
     if ((size_t)(p->nyp - 1) * (p->nxp - 1) >= ((size_t)1 << 23)) return 0;   // column index must fit a mantissa
     if ((size_t)(p->nyp - 1) * (p->nxp - 1) * quad_zq(p) * sizeof(float4) >= ((size_t)1 << 32)) return 0;
     return (size_t)n_channels * (size_t)(p->nyp - 1) * (p->nxp - 1) * quad_zq(p) * sizeof(float4);
@@ -374,8 +352,28 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
     a.acc = p->geo.accuracy;
     a.dX = (float)p->geo.dVoxelX; a.dY = (float)p->geo.dVoxelY; a.dZ = (float)p->geo.dVoxelZ;
     a.a0 = epi->a0; a.a1 = epi->a1; a.c = epi->c;
+    a.accumulate = 0;
     a.whx = epi->w_half_x; a.why = epi->w_half_y; a.whz = epi->w_half_z; a.wthr = epi->w_thr;
+    a.fan_rows = 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pax_plan_projector(p) == PAX_PROJECTOR_FAN) {
+        // one channel per launch; a second channel is a first pass whose result the second adds to
+        if (vol_res1) {
+            AxArgs a1 = a;
+            a1.vol0 = vol_res1; a1.vol1 = nullptr; a1.nsamples = nullptr; a1.maxout = nullptr;
+            a1.c = 0.f; a1.accumulate = 0;
+            if (epi->out1) { a1.out = epi->out1; a1.a0 = 1.f; }
+            else { a1.a0 = epi->a1; }
+            int rc = pax_ax_fan_launch(p, a1, PAX_AX_PLAIN, count, st);
+            if (rc != PAX_OK) return rc;
+            a.accumulate = epi->out1 ? 0 : 1;
+        }
+        a.vol1 = nullptr; a.out1 = nullptr;
+        int rc = pax_ax_fan_launch(p, a, epi->mode, count, st);
+        if (rc != PAX_OK) return rc;
+        PAX_CHECK_CUDA(cudaGetLastError());
+        return PAX_OK;
+    }
     if (workspace) {
         PAX_REQUIRE(((uintptr_t)workspace & 15) == 0, "pax_ax: workspace must be 16-byte aligned");
         const int nyq = p->nyp - 1, nxq = p->nxp - 1, zq = quad_zq(p);

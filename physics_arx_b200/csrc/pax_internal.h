@@ -36,7 +36,43 @@ struct PaxPlan {
     size_t vol_elems;
     AngleDev *d_angles;
     std::vector<AngleDev> h_angles;
+    int projector;              // PAX_PROJECTOR_* requested (AUTO resolves per call)
+    int fan_rows;               // ax_fan.cu row tile that keeps every z window within 32 levels (0: none)
+    int fan_warps;              // warps per CTA for that tile
+    double fan_run;             // mean length (rows) of the equal-n runs of a detector column
 };
+
+
+// arguments shared by the two forward-projector kernels (ax.cu ray march, ax_fan.cu fan planes)
+struct AxArgs {
+    const AngleDev *angles;
+    const float *vol0;
+    const float *vol1;
+    const char *quad0;            // quad-packed channels
+    const char *quad1;
+    int qshift;                   // log2 of the quad column stride in bytes
+    float nxq_f;                  // quad columns per y row
+    float *out;
+    float *out1;
+    const float *b;
+    double *sumsq;
+    unsigned long long *nsamples;
+    unsigned *maxout;
+    int first, nv, nu;
+    int nxp, nzp;                 // resident strides: x -> nzp, y -> nxp*nzp
+    float hix, hiy, hiz;          // exclusive upper bounds of valid padded coordinates
+    float loz;                    // inclusive lower z bound (PAX_ZOFF-1); x,y lower bound is 0
+    double acc;
+    float dX, dY, dZ;
+    float a0, a1, c;
+    float whx, why, whz, wthr;
+    int fan_rows;                 // ax_fan.cu: detector rows per CTA tile
+    int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
+};
+
+// ax_fan.cu
+int pax_fan_configure(PaxPlan *p);
+int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a, int mode, int count, cudaStream_t st);
 
 int pax_set_error(int code, const char *fmt, ...);
 

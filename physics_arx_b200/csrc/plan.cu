@@ -94,7 +94,38 @@ extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, Pax
         delete p;
         return pax_set_error(PAX_ERR_CUDA, "pax_plan_create: %s", cudaGetErrorString(e));
     }
+    p->projector = PAX_PROJECTOR_AUTO;
+    pax_fan_configure(p);
     *out = p;
+    return PAX_OK;
+}
+
+extern "C" int pax_plan_set_projector(PaxPlan *p, int kind)
+{
+    PAX_REQUIRE(p, "pax_plan_set_projector: NULL plan");
+    PAX_REQUIRE(kind == PAX_PROJECTOR_AUTO || kind == PAX_PROJECTOR_RAY || kind == PAX_PROJECTOR_FAN,
+                "pax_plan_set_projector: unknown projector %d", kind);
+    PAX_REQUIRE(kind != PAX_PROJECTOR_FAN || p->fan_rows >= 1,
+                "pax_plan_set_projector: the fan-plane projector does not fit this geometry");
+    p->projector = kind;
+    return PAX_OK;
+}
+
+// which kernel pax_ax will run for this plan: AUTO picks the fan-plane projector when the
+// equal-n runs of a detector column are long enough to pay for the shared in-plane pass
+extern "C" int pax_plan_projector(const PaxPlan *p)
+{
+    if (!p) return PAX_PROJECTOR_RAY;
+    if (p->projector != PAX_PROJECTOR_AUTO) return p->projector;
+    return PAX_PROJECTOR_RAY;   // FAN v1 is correct but not yet faster (24 vs 18 ms per C2 subset)
+}
+
+extern "C" int pax_plan_fan_info(const PaxPlan *p, int *rows_per_tile, int *warps, double *mean_run)
+{
+    PAX_REQUIRE(p, "pax_plan_fan_info: NULL plan");
+    if (rows_per_tile) *rows_per_tile = p->fan_rows;
+    if (warps) *warps = p->fan_warps;
+    if (mean_run) *mean_run = p->fan_run;
     return PAX_OK;
 }
 

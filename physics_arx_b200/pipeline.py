@@ -70,7 +70,7 @@ class SCBCTPipeline:
         m = self._max
         if self.n_local:
             p.ax(self.ct_res, 0, self.n_local, out=st.b, maxout=m)     # max(p) fused in the epilogue
-            self.launches += 3                                          # quad pack, projector, decode
+            self.launches += p.ax_launches(1) + 1                       # (quad pack,) projector, decode
         else:
             m.fill_(-3e38)
         if self.group is not None:

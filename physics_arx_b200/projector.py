@@ -47,7 +47,7 @@ class Plan:
     whole run so that Ax and Atb never convert.
     """
 
-    def __init__(self, geo: Geometry, angles, device=None):
+    def __init__(self, geo: Geometry, angles, device=None, projector=None):
         if not torch.cuda.is_available():
             raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
         self.lib = _lib.load()
@@ -68,7 +68,12 @@ class Plan:
         self._h = handle
         self.vol_elems = int(self.lib.pax_vol_elems(self._h))
         self._work = None              # Ax scratch (quad-packed volume), grown on demand
-        self.use_workspace = os.environ.get("PAX_AX_KERNEL", "quad") != "plain"
+        # PAX_AX_KERNEL / projector=: auto (default) | fan | ray (= quad) | plain  (include/pax.h)
+        kind = (projector or os.environ.get("PAX_AX_KERNEL", "auto")).lower()
+        if kind not in ("auto", "fan", "ray", "quad", "plain"):
+            raise ValueError(f"unknown projector {kind!r}")
+        self.use_workspace = kind != "plain"
+        self.set_projector({"auto": "auto", "fan": "fan"}.get(kind, "ray"))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -78,6 +83,29 @@ class Plan:
             except Exception:
                 pass
             self._h = None
+
+    def set_projector(self, kind):
+        """'auto' | 'ray' | 'fan': which forward-projector kernel pax_ax runs (include/pax.h)."""
+        code = {"auto": _lib.PAX_PROJECTOR_AUTO, "ray": _lib.PAX_PROJECTOR_RAY,
+                "fan": _lib.PAX_PROJECTOR_FAN}[kind]
+        _lib.check(self.lib.pax_plan_set_projector(self._h, code), "pax_plan_set_projector")
+
+    @property
+    def projector(self):
+        return {_lib.PAX_PROJECTOR_RAY: "ray", _lib.PAX_PROJECTOR_FAN: "fan"}[
+            int(self.lib.pax_plan_projector(self._h))]
+
+    def fan_info(self):
+        rows, warps, run = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        _lib.check(self.lib.pax_plan_fan_info(self._h, ctypes.byref(rows), ctypes.byref(warps),
+                                              ctypes.byref(run)), "pax_plan_fan_info")
+        return {"rows_per_tile": rows.value, "warps": warps.value, "mean_run": run.value}
+
+    def ax_launches(self, channels=1):
+        """kernels one pax_ax call launches (bench.py's gpu_launches claim)."""
+        if self.projector == "fan":
+            return channels
+        return 1 + (channels if self._workspace(channels) is not None else 0)
 
     # ------------------------------------------------------------------ volumes
     def new_volume(self):

@@ -183,3 +183,111 @@ def test_plain_and_quad_gather_backends_agree(oracle):
     b = plan.ax(res).cpu().numpy()
     assert rel_l2(a, b) <= 2e-6
     assert rel_l2(a, oracle.ax(vol.cpu().numpy(), geo, angles)) <= PROJ_TOL
+
+
+# ----------------------------------------------------------------------- fan-plane projector
+def _fan_cases():
+    """Geometries for the FAN kernel (csrc/ax_fan.cu): fine detector rows over thick slices so that
+    runs of equal n are long (the C2 regime, scaled down), plus the generic cases, where runs are a
+    few rows long and the kernel is merely correct."""
+    from physics_arx_b200.phantom import make_geometry
+    out = list(_cases()[:2])
+    # C2-like: 2.5 mm slices, 0.5 mm rows, half-fan, z-truncated, several row tiles and runs
+    out.append(("c2like", make_geometry((24, 48, 48), (2.5, 1.0, 1.0), (300, 72), (0.5, 1.6),
+                                         off_detector=(0.0, -20.0)),
+                np.linspace(0, 2 * np.pi, 5, endpoint=False) + 0.3))
+    # vertical detector offset (rays all tilted one way), volume offset, odd counts
+    g = make_geometry((19, 33, 29), (3.0, 1.5, 2.0), (157, 41), (0.7, 2.0), off_detector=(25.0, 5.0))
+    g.offOrigin = np.array((6.0, -4.0, 3.0))
+    out.append(("tilted", g, np.array([0.0, 0.9, 2.2, 3.9, 5.5])))
+    return out
+
+
+@pytest.mark.parametrize("name,geo,angles", _fan_cases(), ids=[c[0] for c in _fan_cases()])
+def test_fan_projector_matches_oracle(oracle, name, geo, angles):
+    torch = _torch()
+    from physics_arx_b200.projector import Plan
+    rng = np.random.default_rng(11)
+    vol = rng.random(tuple(int(v) for v in geo.nVoxel)).astype(np.float32)
+    plan = Plan(geo, angles, projector="fan")
+    assert plan.projector == "fan" and plan.fan_info()["rows_per_tile"] >= 1
+    res = plan.pack(torch.from_numpy(vol).cuda())
+    ns = torch.zeros(1, dtype=torch.int64, device="cuda")
+    m = torch.zeros(1, device="cuda")
+    got = plan.ax(res, nsamples=ns, maxout=m)
+    ref, nref = oracle.ax(vol, geo, angles, return_counts=True)
+    assert rel_l2(got.cpu().numpy(), ref) <= PROJ_TOL, rel_l2(got.cpu().numpy(), ref)
+    assert rel_l2(got.cpu().numpy(), ref) <= 2e-6            # it is the same sum, re-associated
+    assert float(m.item()) == float(got.max().item())
+    assert abs(int(ns.item()) - int(nref.sum())) <= 1e-5 * nref.sum() + 2 * got.numel() / len(angles)
+    # and the ray kernel on the same plan gives the same projections
+    plan.set_projector("ray")
+    ray = plan.ax(res)
+    assert rel_l2(got.cpu().numpy(), ray.cpu().numpy()) <= 2e-6
+
+
+def test_fan_projector_residual_and_two_channel(oracle):
+    torch = _torch()
+    from physics_arx_b200.projector import Plan
+    name, geo, angles = _fan_cases()[2]
+    rng = np.random.default_rng(12)
+    shape = tuple(int(v) for v in geo.nVoxel)
+    ct = rng.random(shape).astype(np.float32)
+    art = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+    plan = Plan(geo, angles, projector="fan")
+    r0, r1 = plan.pack(torch.from_numpy(ct).cuda()), plan.pack(torch.from_numpy(art).cuda())
+    ref = oracle.ax(ct.astype(np.float64) + 0.7 * art.astype(np.float64), geo, angles)
+    got = plan.ax(r0, res1=r1, a0=1.0, a1=0.7)
+    assert rel_l2(got.cpu().numpy(), ref) <= 2e-6
+    p1 = torch.empty_like(got)
+    p0 = plan.ax(r0, res1=r1, out1=p1)
+    assert rel_l2((p0 + 0.7 * p1).cpu().numpy(), ref) <= 2e-6
+    # residual epilogue: W*(b - Ax(x)) and the running sum of squares, against the ray kernel
+    b = (got * 1.1).contiguous()
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    out = torch.empty_like(got)
+    plan.ax_residual(r0, b, 0, len(angles), out, sumsq=ss)
+    w = plan.compute_w()
+    want = w * (b - plan.ax(r0))
+    assert rel_l2(out.cpu().numpy(), want.cpu().numpy()) <= 1e-6
+    assert abs(float(ss.item()) - float(((b - plan.ax(r0)) ** 2).sum().item())) <= 1e-5 * float(ss.item())
+
+
+def test_ossart_with_fan_projector_matches_oracle(oracle):
+    import physics_arx_b200 as pax
+    from physics_arx_b200.phantom import lung_phantom, make_geometry
+    import os
+    geo = make_geometry((20, 40, 40), (2.5, 1.0, 1.0), (200, 64), (0.5, 1.5), off_detector=(0.0, -15.0))
+    angles = np.linspace(0, 2 * np.pi, 24)
+    vol = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    b = oracle.ax(vol, geo, angles).astype(np.float32)
+    ref = oracle.ossart(b, geo, angles, 3, blocksize=5)
+    os.environ["PAX_AX_KERNEL"] = "fan"
+    try:
+        got = pax.algorithms.ossart(b, geo, angles, 3, blocksize=5)
+    finally:
+        del os.environ["PAX_AX_KERNEL"]
+    d = np.abs(got.astype(np.float64) - ref) * HU
+    assert d.mean() <= 1.0 and d.max() <= 5.0, (d.mean(), d.max())
+
+
+def test_full_size_c2_projection_matches_oracle(oracle):
+    """BASELINE.json's full C2 geometry (512x512x128, 1024x768 half-fan): three angles of the phantom's
+    projections against the float64 oracle, for both projector kernels."""
+    torch = _torch()
+    from physics_arx_b200.phantom import config_c2, lung_phantom
+    from physics_arx_b200.projector import Plan
+    cfg = config_c2()
+    geo = cfg["geo"]
+    angles = cfg["angles"][[3, 250, 601]]
+    vol = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    ref = oracle.ax(vol, geo, angles)
+    plan = Plan(geo, angles)
+    res = plan.pack(torch.from_numpy(vol).cuda())
+    for kind in ("fan", "ray"):
+        plan.set_projector(kind)
+        got = plan.ax(res).cpu().numpy()
+        err = rel_l2(got, ref)
+        print(kind, "rel L2 vs oracle", err, "max abs", np.abs(got - ref).max())
+        assert err <= PROJ_TOL, (kind, err)
+        assert err <= 5e-6, (kind, err)
