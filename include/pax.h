@@ -115,6 +115,9 @@ int pax_plan_projector(const PaxPlan *plan);
 /* tuning facts of the FAN kernel for this geometry: detector rows per CTA tile (0 = does not fit),
  * warps per CTA, mean length in rows of the runs that share one lattice */
 int pax_plan_fan_info(const PaxPlan *plan, int *rows_per_tile, int *warps, double *mean_run);
+/* self-check of the FAN kernel: 1 if any launch so far met a z window wider than its 32 lanes (the
+ * row tile is derived so that this cannot happen); synchronises the device */
+int pax_plan_fault(const PaxPlan *plan);
 
 /* Resident volume layout ("z-column": (Y+2, X+2, Zp) floats, z fastest, zero rim).
  * pax_vol_elems = floats per channel.  pack/unpack convert from/to (Z,Y,X). */

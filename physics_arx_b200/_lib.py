@@ -50,6 +50,7 @@ SYMBOLS = [
     ("pax_plan_projector", ctypes.c_int, [_VP]),
     ("pax_plan_fan_info", ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                          c_double_p]),
+    ("pax_plan_fault", ctypes.c_int, [_VP]),
     ("pax_vol_elems", ctypes.c_size_t, [_VP]),
     ("pax_vol_pack", ctypes.c_int, [_VP, _VP, _VP, _VP]),
     ("pax_vol_unpack", ctypes.c_int, [_VP, _VP, _VP, _VP]),

@@ -39,22 +39,26 @@
 
 #include "pax_internal.h"
 
-#define FAN_K 32           // slices per block window = lanes
-#define FAN_KP 33          // table row stride in float2 (padding against bank conflicts)
-#define FAN_B 32           // steps per warp block
+#define FAN_LQ 8           // lanes (z quads) per step: a chunk's z window is <= 32 slices
+#define FAN_W (4 * FAN_LQ)
+#define FAN_G (32 / FAN_LQ) // streams (runs of consecutive steps) a warp advances at once
+#define FAN_B 8            // steps per stream
+#define FAN_TS (FAN_W + 2) // table row stride in float2 (rows stay 16-byte aligned)
 #define FAN_UC 8           // detector columns per CTA (one 32-byte sector of every output row)
 
 template <int NW>
 struct FanSmem {
-    static constexpr int R = NW * 32;
-    static constexpr int C = NW * FAN_B;
-    float2 T[NW * (FAN_B + 1) * FAN_KP];
-    float4 w[C];
-    int off[C];
+    static constexpr int R = NW * 32;                  // threads; rows per tile <= R
+    static constexpr int NS = NW * FAN_G;              // streams per chunk
+    static constexpr int C = NS * FAN_B;               // steps per chunk
+    static constexpr int TROWS = C + NS;               // one spare row per stream (bank skew)
+    float2 T[TROWS * FAN_TS];                          // running (P,Q) per (step, slice), stream-local
+    float2 carry[NS * FAN_TS];                         // (P,Q) of all earlier streams of the chunk
+    float2 gsum[NW * FAN_W];                           // per-warp totals, input of the carry scan
+    float4 w[C + NS];                                  // bilinear weights per step (stream-padded)
+    int off[C + NS];                                   // in-plane cell offset per step
     int n[R];
-    unsigned starts[NW];          // bit r of word w: row 32w+r starts a run of equal n
-    float out[FAN_UC * R];
-    int kA[NW];
+    unsigned starts[NW];                               // bit r of word w: row 32w+r starts a run of equal n
     int red[2];
 };
 
@@ -85,12 +89,28 @@ __device__ __forceinline__ void fan_slab(double s, double d, double lo, double h
     }
 }
 
+__device__ __forceinline__ float4 fan_ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// inclusive running (P,Q) of chunk-local step i (i >= 0) at table column c and c+1
+__device__ __forceinline__ void fan_lookup(const float2 *T, const float2 *carry, int i, int c, float2 &lo,
+                                           float2 &hi)
+{
+    const int s = i >> 3;                              // FAN_B == 8
+    const float2 *t = T + (i + s) * FAN_TS + c;
+    const float2 *k = carry + s * FAN_TS + c;
+    const float2 t0 = t[0], t1 = t[1], k0 = k[0], k1 = k[1];
+    lo = make_float2(t0.x + k0.x, t0.y + k0.y);
+    hi = make_float2(t1.x + k1.x, t1.y + k1.y);
+}
+
 template <int NW, int MODE>
 __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
 {
-    constexpr int R = NW * 32, C = NW * FAN_B, B = FAN_B, KP = FAN_KP;
+    using SM = FanSmem<NW>;
+    constexpr int R = SM::R, C = SM::C, NS = SM::NS, B = FAN_B, TS = FAN_TS, W = FAN_W;
+    static_assert(FAN_B == 8, "fan_lookup assumes 8 steps per stream");
     extern __shared__ __align__(16) unsigned char fan_smem_raw[];
-    FanSmem<NW> &sm = *reinterpret_cast<FanSmem<NW> *>(fan_smem_raw);
+    SM &sm = *reinterpret_cast<SM *>(fan_smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ia = blockIdx.y;
@@ -101,11 +121,18 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
     const double sx = A.sx, sy = A.sy, sz = A.sz;
     const double dz = A.oz + (double)(V0 + tid) * A.vz - sz;      // this thread's row
     const double zlo = (double)a.loz, zhi = (double)a.hiz;
-    const int kmin = (int)a.loz, kmax = (int)a.hiz;               // slices that can be non-zero: [kmin+1, kmax-1]
+    const int kmin = (int)a.loz, kmax = (int)a.hiz;               // slices a sample can touch: [kmin, kmax]
+    const float kminf = a.loz, kmaxf = a.hiz;
     const int sxs = a.nzp, sys = a.nxp * a.nzp;
+    // phase-1 role of this lane: stream g of the warp, z quad q of the window
+    const int g = lane / FAN_LQ, q = lane % FAN_LQ;
+    const int strm = warp * FAN_G + g;
     unsigned my_ns = 0;
+    float r2 = 0.f, mymax = -INFINITY;
 
+#pragma unroll 1
     for (int uc = 0; uc < ucn; ++uc) {
+        float sum = 0.f, steplen = 0.f;
         const int u = blockIdx.x * FAN_UC + uc;
         const double dx = A.ox + u * A.ux - sx, dy = A.oy + u * A.uy - sy;
         const double dxy2 = dx * dx + dy * dy;
@@ -118,7 +145,6 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
             if (lane == 0) sm.starts[warp] = bal;
         }
         __syncthreads();
-        float sum = 0.f, steplen = 0.f;
         int cur = 0;
         while (cur < nRows) {
             // ---- the run of rows [cur, e) that share n (uniform over the CTA)
@@ -161,14 +187,16 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                 const double dzB = (A.oz + (double)(V0 + e - 1) * A.vz - sz) * rn;
                 const float fdz = (float)ddz;
                 const float inv = 1.f / fabsf(fdz);
+#pragma unroll 1
                 for (int c0 = I0; c0 <= I1; c0 += C) {
-                    // ---- phase 0: one step per thread
+                    const int nst = min(C, I1 - c0 + 1);          // steps of this chunk
+                    // ---- phase 0: every thread prepares steps (in-plane cell + bilinear weights)
                     for (int t = tid; t < C; t += R) {
-                        const int j = c0 + t;
                         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
                         int off = 0;
-                        if (j <= I1) {
-                            const float qx = (float)(sx + (double)j * ddx), qy = (float)(sy + (double)j * ddy);
+                        if (t < nst) {
+                            const double j = (double)(c0 + t);
+                            const float qx = (float)(sx + j * ddx), qy = (float)(sy + j * ddy);
                             const float cx = fminf(fmaxf(floorf(qx), 0.f), a.hix - 1.f);
                             const float cy = fminf(fmaxf(floorf(qy), 0.f), a.hiy - 1.f);
                             const float fx = fminf(fmaxf(qx - cx, 0.f), 1.f), fy = fminf(fmaxf(qy - cy, 0.f), 1.f);
@@ -176,83 +204,136 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                             const float gx = 1.f - fx, gy = 1.f - fy;
                             w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
                         }
-                        sm.w[t] = w;
-                        sm.off[t] = off;
+                        sm.w[t + (t >> 3)] = w;
+                        sm.off[t + (t >> 3)] = off;
                     }
-                    // ---- z window of this warp's block of steps
-                    const int jb = c0 + warp * B;
-                    const int jl = min(jb + B - 1, I1);
-                    int kA = 0, kB = -1;
-                    if (jb <= I1) {
-                        const double z0 = sz + (double)jb * dzA, z1 = sz + (double)jb * dzB;
-                        const double z2 = sz + (double)jl * dzA, z3 = sz + (double)jl * dzB;
+                    // ---- z window of the chunk: all rows of the run x all its steps (uniform)
+                    int kA, nq;
+                    {
+                        const double ja = (double)c0, jb = (double)(c0 + nst - 1);
+                        const double z0 = sz + ja * dzA, z1 = sz + ja * dzB, z2 = sz + jb * dzA, z3 = sz + jb * dzB;
                         const double zmin = fmin(fmin(z0, z1), fmin(z2, z3));
                         const double zmax = fmax(fmax(z0, z1), fmax(z2, z3));
-                        kA = max(kmin, (int)floor(zmin - 1e-3));
-                        kB = min(kmax, (int)floor(zmax + 1e-3) + 1);
+                        kA = max(kmin, (int)floor(zmin - 1e-3)) & ~3;
+                        const int kB = min(kmax, (int)floor(zmax + 1e-3) + 1);
+                        nq = (kB - kA + 4) >> 2;                  // quads in the window; <= FAN_LQ by the
+                        if (nq > FAN_LQ && tid == 0 && a.fault)   // row tile pax_fan_configure chose
+                            atomicExch(a.fault, 1);
                     }
-                    if (lane == 0) sm.kA[warp] = kA;
                     __syncthreads();
-                    // ---- phase 1: running sums of G over the block, one slice per lane
-                    if (kB >= kA) {
-                        const int k = kA + lane;
-                        const bool on = k <= kB;
-                        const float *__restrict__ base = a.vol0 + k;
-                        float2 *Tw = sm.T + warp * (B + 1) * KP + lane;
-                        Tw[0] = make_float2(0.f, 0.f);
-                        float P = 0.f, Q = 0.f;
-                        const int nst = jl - jb + 1;
-                        const float4 *wp = sm.w + warp * B;
-                        const int *op = sm.off + warp * B;
-#pragma unroll 4
-                        for (int s = 0; s < nst; ++s) {
-                            const float4 w = wp[s];
-                            const int off = op[s];
-                            float g = 0.f;
-                            if (on) {
-                                const float *p = base + off;
-                                g = w.x * __ldg(p);
-                                g = fmaf(w.y, __ldg(p + sxs), g);
-                                g = fmaf(w.z, __ldg(p + sys), g);
-                                g = fmaf(w.w, __ldg(p + sys + sxs), g);
+                    // ---- phase 1: stream-local running sums, four slices per lane
+                    {
+                        const bool on = q < nq;
+                        const float *__restrict__ base = a.vol0 + kA + 4 * q;
+                        float4 P = make_float4(0.f, 0.f, 0.f, 0.f), Q = P;
+                        float4 c00 = P, c01 = P, c10 = P, c11 = P;
+                        int poff = -1;
+                        const int i_first = strm * B;
+                        const float4 *wp = sm.w + i_first + strm;
+                        const int *op = sm.off + i_first + strm;
+                        float4 *Tw = reinterpret_cast<float4 *>(sm.T + (i_first + strm) * TS + 4 * q);
+                        float jf = (float)(i_first - C / 2);
+                        if (i_first < nst) {
+#pragma unroll 2
+                            for (int s = 0; s < B; ++s) {
+                                const float4 w = wp[s];
+                                const int off = op[s];
+                                if (on && off != poff) {
+                                    const float *p = base + off;
+                                    c00 = fan_ld4(p); c01 = fan_ld4(p + sxs);
+                                    c10 = fan_ld4(p + sys); c11 = fan_ld4(p + sys + sxs);
+                                }
+                                poff = off;
+                                float4 v;
+                                v.x = fmaf(w.w, c11.x, fmaf(w.z, c10.x, fmaf(w.y, c01.x, w.x * c00.x)));
+                                v.y = fmaf(w.w, c11.y, fmaf(w.z, c10.y, fmaf(w.y, c01.y, w.x * c00.y)));
+                                v.z = fmaf(w.w, c11.z, fmaf(w.z, c10.z, fmaf(w.y, c01.z, w.x * c00.z)));
+                                v.w = fmaf(w.w, c11.w, fmaf(w.z, c10.w, fmaf(w.y, c01.w, w.x * c00.w)));
+                                P.x += v.x; P.y += v.y; P.z += v.z; P.w += v.w;
+                                Q.x = fmaf(jf, v.x, Q.x); Q.y = fmaf(jf, v.y, Q.y);
+                                Q.z = fmaf(jf, v.z, Q.z); Q.w = fmaf(jf, v.w, Q.w);
+                                jf += 1.f;
+                                if (on) {
+                                    Tw[s * (TS / 2)] = make_float4(P.x, Q.x, P.y, Q.y);
+                                    Tw[s * (TS / 2) + 1] = make_float4(P.z, Q.z, P.w, Q.w);
+                                }
                             }
-                            P += g;
-                            Q = fmaf((float)s, g, Q);
-                            Tw[(s + 1) * KP] = make_float2(P, Q);
+                        }
+                        // stream totals -> warp totals (exclusive over the warp's streams = carry within warp)
+                        // lanes of stream g hold its totals for quad q; scan over g with shuffles
+                        float4 cP = make_float4(0.f, 0.f, 0.f, 0.f), cQ = cP;      // sum of earlier streams of this warp
+                        float4 tP = P, tQ = Q;                                     // running inclusive
+#pragma unroll
+                        for (int d = FAN_LQ; d < 32; d <<= 1) {
+                            float4 oP, oQ;
+                            oP.x = __shfl_up_sync(0xffffffffu, tP.x, d); oP.y = __shfl_up_sync(0xffffffffu, tP.y, d);
+                            oP.z = __shfl_up_sync(0xffffffffu, tP.z, d); oP.w = __shfl_up_sync(0xffffffffu, tP.w, d);
+                            oQ.x = __shfl_up_sync(0xffffffffu, tQ.x, d); oQ.y = __shfl_up_sync(0xffffffffu, tQ.y, d);
+                            oQ.z = __shfl_up_sync(0xffffffffu, tQ.z, d); oQ.w = __shfl_up_sync(0xffffffffu, tQ.w, d);
+                            if (lane >= d) {
+                                tP.x += oP.x; tP.y += oP.y; tP.z += oP.z; tP.w += oP.w;
+                                tQ.x += oQ.x; tQ.y += oQ.y; tQ.z += oQ.z; tQ.w += oQ.w;
+                            }
+                        }
+                        cP = make_float4(tP.x - P.x, tP.y - P.y, tP.z - P.z, tP.w - P.w);
+                        cQ = make_float4(tQ.x - Q.x, tQ.y - Q.y, tQ.z - Q.z, tQ.w - Q.w);
+                        // park the in-warp carry; the cross-warp part is added after the barrier
+                        float4 *cw = reinterpret_cast<float4 *>(sm.carry + strm * TS + 4 * q);
+                        cw[0] = make_float4(cP.x, cQ.x, cP.y, cQ.y);
+                        cw[1] = make_float4(cP.z, cQ.z, cP.w, cQ.w);
+                        if (g == FAN_G - 1) {                      // last stream's inclusive total = warp total
+                            float4 *gw = reinterpret_cast<float4 *>(sm.gsum + warp * W + 4 * q);
+                            gw[0] = make_float4(tP.x, tQ.x, tP.y, tQ.y);
+                            gw[1] = make_float4(tP.z, tQ.z, tP.w, tQ.w);
                         }
                     }
                     __syncthreads();
-                    // ---- phase 2: one detector row per thread
+                    // ---- carry across warps: thread (stream s, column c) adds the totals of earlier warps
+                    for (int t = tid; t < NS * W; t += R) {
+                        const int s = t / W, c = t % W;
+                        const int ws = s / FAN_G;
+                        float2 acc = sm.carry[s * TS + c];
+                        for (int w2 = 0; w2 < ws; ++w2) {
+                            const float2 o = sm.gsum[w2 * W + c];
+                            acc.x += o.x; acc.y += o.y;
+                        }
+                        sm.carry[s * TS + c] = acc;
+                    }
+                    __syncthreads();
+                    // ---- phase 2: one detector row per thread, one table look-up pair per stretch end
                     if (valid) {
                         const int lo = max(i0, c0) - c0, hi = min(i1, c0 + C - 1) - c0;   // chunk-local steps
                         if (lo <= hi) {
                             const float zc0 = (float)(sz + (double)c0 * ddz);
-                            for (int w2 = lo / B; w2 <= hi / B; ++w2) {
-                                const int jb2 = w2 * B;
-                                const int bl = min(hi, jb2 + B - 1);
-                                const int kAw = sm.kA[w2];
-                                const float2 *Tb = sm.T + w2 * (B + 1) * KP;
-                                int j = max(lo, jb2);
-                                while (j <= bl) {
-                                    const float zl = fmaf((float)j, fdz, zc0);
-                                    const float kf = floorf(zl);
-                                    const float tt = zl - kf;
-                                    // steps that stay in slice pair (k, k+1)
-                                    int m;
-                                    if (fdz > 0.f) m = (int)fminf(ceilf((1.f - tt) * inv), 1.0e4f) - 1;
-                                    else if (fdz < 0.f) m = (int)fminf(floorf(tt * inv), 1.0e4f);
-                                    else m = B;
-                                    const int je = min(bl, j + max(m, 0));
-                                    const int r0 = j - jb2, r1 = je - jb2 + 1;
-                                    const int kk = min(max((int)kf - kAw, 0), FAN_K - 2);
-                                    const float2 A0 = Tb[r0 * KP + kk], A1 = Tb[r1 * KP + kk];
-                                    const float2 B0 = Tb[r0 * KP + kk + 1], B1 = Tb[r1 * KP + kk + 1];
-                                    const float dP0 = A1.x - A0.x, dQ0 = A1.y - A0.y;
-                                    const float dP1 = B1.x - B0.x, dQ1 = B1.y - B0.y;
-                                    const float alpha = fmaf(-(float)r0, fdz, tt);
-                                    sum += fmaf(fdz, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
-                                    j = je + 1;
+                            const float jc = (float)(C / 2);
+                            int j = lo;
+                            // running sums just before the first step
+                            float zl = fmaf((float)j, fdz, zc0);
+                            while (j <= hi) {
+                                // fp32 z may round onto the clip bounds the double range excluded: keep the
+                                // slice pair inside [kmin, kmax] (tt then extrapolates by an ulp)
+                                const float kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
+                                const float tt = zl - kf;
+                                // steps that stay in slice pair (k, k+1)
+                                int m;
+                                if (fdz > 0.f) m = (int)fminf(ceilf((1.f - tt) * inv), 1.0e4f) - 1;
+                                else if (fdz < 0.f) m = (int)fminf(floorf(tt * inv), 1.0e4f);
+                                else m = C;
+                                const int je = min(hi, j + max(m, 0));
+                                int kk = (int)kf - kA;
+                                if (kk < 0 || kk > 4 * nq - 2) {               // cannot happen: see pax_fan_configure
+                                    if (a.fault) atomicExch(a.fault, 2);
+                                    kk = min(max(kk, 0), W - 2);
                                 }
+                                float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0, b1;
+                                if (j > 0) fan_lookup(sm.T, sm.carry, j - 1, kk, a0, a1);
+                                fan_lookup(sm.T, sm.carry, je, kk, b0, b1);
+                                const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
+                                const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
+                                const float alpha = fmaf(jc - (float)j, fdz, tt);      // t at index C/2
+                                sum += fmaf(fdz, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
+                                j = je + 1;
+                                zl = fmaf((float)j, fdz, zc0);
                             }
                         }
                     }
@@ -263,30 +344,25 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
             }
             cur = e;
         }
-        sm.out[uc * R + tid] = sum * steplen;
-    }
-    __syncthreads();
-
-    // ---- epilogue, transposed so that a thread group writes whole 32-byte sectors of a row
-    float r2 = 0.f, mymax = -INFINITY;
-    for (int el = tid; el < nRows * FAN_UC; el += R) {
-        const int row = el / FAN_UC, uc = el % FAN_UC;
-        if (uc >= ucn) continue;
-        const int v = V0 + row, u = blockIdx.x * FAN_UC + uc;
-        const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
-        const float p0 = sm.out[uc * R + row];
-        if (MODE == PAX_AX_PLAIN) {
-            float val = a.a0 * p0;
-            if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
-            if (a.accumulate) val += a.out[o];
-            a.out[o] = val;
-            mymax = fmaxf(mymax, val);
-        } else {
-            const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
-            const float w = L > a.wthr ? 1.f / L : 0.f;
-            const float r = __ldg(a.b + o) - p0;
-            r2 = fmaf(r, r, r2);
-            a.out[o] = w * r;
+        // ---- epilogue of this column for this thread's row.  The eight columns of the CTA fill one
+        // 32-byte sector of the row between them; L2 merges the partial writes.
+        if (tid < nRows) {
+            const int v = V0 + tid;
+            const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
+            const float p0 = sum * steplen;
+            if (MODE == PAX_AX_PLAIN) {
+                float val = a.a0 * p0;
+                if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
+                if (a.accumulate) val += a.out[o];
+                a.out[o] = val;
+                mymax = fmaxf(mymax, val);
+            } else {
+                const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
+                const float w = L > a.wthr ? 1.f / L : 0.f;
+                const float r = __ldg(a.b + o) - p0;
+                r2 = fmaf(r, r, r2);
+                a.out[o] = w * r;
+            }
         }
     }
     if (a.nsamples) {
@@ -315,26 +391,36 @@ int pax_fan_configure(PaxPlan *p)
     const double vz = g.dDetecV / g.dVoxelZ;
     const double dmax = std::fmax(g.dVoxelX, g.dVoxelY);
     const double hx = 0.5 * g.nVoxelX * g.dVoxelX, hy = 0.5 * g.nVoxelY * g.dVoxelY;
+    // tau: largest fraction of a ray's length at which it can still be inside the volume (far corner);
+    // slope: largest |dz| per step of any ray, in slices
     double tau = 0.0, slope = 0.0;
     for (const AngleDev &A : p->h_angles) {
-        const double r = std::sqrt((hx + std::fabs(A.offOX) + g.dVoxelX) * (hx + std::fabs(A.offOX) + g.dVoxelX) +
-                                   (hy + std::fabs(A.offOY) + g.dVoxelY) * (hy + std::fabs(A.offOY) + g.dVoxelY));
-        tau = std::fmax(tau, std::fmin(1.0, ((double)A.DSO + r) / (double)A.DSD));
+        const double rx = hx + std::fabs(A.offOX) + g.dVoxelX, ry = hy + std::fabs(A.offOY) + g.dVoxelY;
+        tau = std::fmax(tau, std::fmin(1.0, ((double)A.DSO + std::sqrt(rx * rx + ry * ry)) / (double)A.DSD));
         const double nmin = std::ceil((double)A.DSD / dmax / g.accuracy);
         const double za = std::fabs(A.oz - A.sz), zb = std::fabs(A.oz + (g.nDetecV - 1) * A.vz - A.sz);
         slope = std::fmax(slope, std::fmax(za, zb) / nmin);
     }
-    const double room = (double)FAN_K - 3.2 - FAN_B * slope;
-    int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
-    rows = std::min(rows, std::min(256, (int)g.nDetecV));
+    // window of a chunk <= rows*vz*tau (spread of the rows) + steps*slope (travel) + 2 (floor, +1)
+    //                      + 3 (alignment to a quad) must fit FAN_W slices
     p->fan_rows = 0;
     p->fan_warps = 0;
-    if (rows >= 1) {
-        // whole warps of rows when the tile is large: no idle lanes in phase 2
-        if (rows >= 32 && rows < (int)g.nDetecV) rows = rows / 32 * 32;
-        const int nw = rows > 192 ? 8 : rows > 128 ? 6 : 4;
-        p->fan_rows = rows;
-        p->fan_warps = nw;
+    const int nws[3] = {8, 6, 4};
+    const char *force = getenv("PAX_FAN_WARPS");               // tuning hook
+    for (int c = 0; c < 3; ++c) {
+        const int nw = nws[c], steps = nw * FAN_G * FAN_B;
+        if (force && atoi(force) != nw) continue;
+        const double room = (double)FAN_W - 5.3 - steps * slope;
+        int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
+        rows = std::min(rows, std::min(nw * 32, (int)g.nDetecV));
+        if (rows < 1) continue;
+        // equal tiles; prefer the configuration that keeps the most threads busy in phase 2
+        const int tiles = (g.nDetecV + rows - 1) / rows;
+        rows = (g.nDetecV + tiles - 1) / tiles;
+        if (p->fan_rows == 0 || rows * p->fan_warps > p->fan_rows * nw) {
+            p->fan_rows = rows;
+            p->fan_warps = nw;
+        }
     }
     // mean run length of equal n over three columns of the first angle
     {
@@ -371,8 +457,10 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
 {
     AxArgs a = a0;
     a.fan_rows = p->fan_rows;
+    a.fault = p->d_fault;
+    PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
     PAX_REQUIRE(p->fan_rows >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
-                                  "(z window of a single detector row exceeds %d slices)", FAN_K);
+                                  "(z window of a single detector row exceeds %d slices)", FAN_W);
     const bool plain = mode == PAX_AX_PLAIN;
     switch (p->fan_warps) {
     case 4: return plain ? fan_launch<4, PAX_AX_PLAIN>(a, count, st) : fan_launch<4, PAX_AX_RESIDUAL>(a, count, st);

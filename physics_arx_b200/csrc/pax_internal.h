@@ -40,6 +40,7 @@ struct PaxPlan {
     int fan_rows;               // ax_fan.cu row tile that keeps every z window within 32 levels (0: none)
     int fan_warps;              // warps per CTA for that tile
     double fan_run;             // mean length (rows) of the equal-n runs of a detector column
+    int *d_fault;               // device word the fan kernel raises if a z window overflowed
 };
 
 
@@ -68,6 +69,7 @@ struct AxArgs {
     float whx, why, whz, wthr;
     int fan_rows;                 // ax_fan.cu: detector rows per CTA tile
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
+    int *fault;                   // ax_fan.cu: set to 1 if a z window did not fit (never, by construction)
 };
 
 // ax_fan.cu

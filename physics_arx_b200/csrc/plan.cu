@@ -86,7 +86,7 @@ extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, Pax
         A.pad_ = 0.f;
     }
     cudaError_t e = cudaGetDevice(&p->device);
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_angles, sizeof(AngleDev) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_angles, sizeof(AngleDev) * n + sizeof(int));
     if (e == cudaSuccess)
         e = cudaMemcpy(p->d_angles, p->h_angles.data(), sizeof(AngleDev) * n, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -94,6 +94,8 @@ extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, Pax
         delete p;
         return pax_set_error(PAX_ERR_CUDA, "pax_plan_create: %s", cudaGetErrorString(e));
     }
+    p->d_fault = reinterpret_cast<int *>(p->d_angles + n);       // same allocation, after the angles
+    cudaMemset(p->d_fault, 0, sizeof(int));
     p->projector = PAX_PROJECTOR_AUTO;
     pax_fan_configure(p);
     *out = p;
@@ -127,6 +129,15 @@ extern "C" int pax_plan_fan_info(const PaxPlan *p, int *rows_per_tile, int *warp
     if (warps) *warps = p->fan_warps;
     if (mean_run) *mean_run = p->fan_run;
     return PAX_OK;
+}
+
+// 1 if a launch of the FAN kernel met a z window wider than its lanes (a bug in the tile choice;
+// results of that launch are wrong).  Synchronises the device.  Test hook.
+extern "C" int pax_plan_fault(const PaxPlan *p)
+{
+    int f = 0;
+    if (!p || cudaMemcpy(&f, p->d_fault, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return f;
 }
 
 extern "C" int pax_plan_destroy(PaxPlan *p)

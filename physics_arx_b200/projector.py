@@ -101,6 +101,10 @@ class Plan:
                                               ctypes.byref(run)), "pax_plan_fan_info")
         return {"rows_per_tile": rows.value, "warps": warps.value, "mean_run": run.value}
 
+    def fault(self):
+        """1 if the fan kernel ever met a z window wider than its lanes on this plan (self-check)."""
+        return int(self.lib.pax_plan_fault(self._h))
+
     def ax_launches(self, channels=1):
         """kernels one pax_ax call launches (bench.py's gpu_launches claim)."""
         if self.projector == "fan":

@@ -218,6 +218,7 @@ def test_fan_projector_matches_oracle(oracle, name, geo, angles):
     ref, nref = oracle.ax(vol, geo, angles, return_counts=True)
     assert rel_l2(got.cpu().numpy(), ref) <= PROJ_TOL, rel_l2(got.cpu().numpy(), ref)
     assert rel_l2(got.cpu().numpy(), ref) <= 2e-6            # it is the same sum, re-associated
+    assert plan.fault() == 0
     assert float(m.item()) == float(got.max().item())
     assert abs(int(ns.item()) - int(nref.sum())) <= 1e-5 * nref.sum() + 2 * got.numel() / len(angles)
     # and the ray kernel on the same plan gives the same projections
@@ -289,5 +290,6 @@ def test_full_size_c2_projection_matches_oracle(oracle):
         got = plan.ax(res).cpu().numpy()
         err = rel_l2(got, ref)
         print(kind, "rel L2 vs oracle", err, "max abs", np.abs(got - ref).max())
+        assert plan.fault() == 0
         assert err <= PROJ_TOL, (kind, err)
         assert err <= 5e-6, (kind, err)

@@ -52,7 +52,8 @@ if args.compare:
         d = outs["fan"] - outs["ray"]
         print(f"fan vs ray: rel L2 {float(d.norm() / outs['ray'].norm()):.3e}, max abs {float(d.abs().max()):.3e} "
               f"(max value {float(outs['ray'].max()):.3f})")
-    p.set_projector("auto")
+    print("fan fault flag:", p.fault())
+    p.set_projector(os.environ.get("PAX_AX_KERNEL", "auto") if os.environ.get("PAX_AX_KERNEL") in ("fan", "ray") else "auto")
 for r in range(args.reps):
     for s in range(len(st.blocks)):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
