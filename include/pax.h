@@ -112,8 +112,9 @@ int pax_plan_n_angles(const PaxPlan *plan);
 #define PAX_PROJECTOR_FAN 2
 int pax_plan_set_projector(PaxPlan *plan, int kind);
 int pax_plan_projector(const PaxPlan *plan);
-/* tuning facts of the FAN kernel for this geometry: detector rows per CTA tile (0 = does not fit),
- * warps per CTA, mean length in rows of the runs that share one lattice */
+/* tuning facts of the FAN kernel for this geometry: most detector rows that are summed from one set of
+ * tables (0 = the kernel does not fit), warps per CTA, mean length in rows of the runs that share one
+ * lattice */
 int pax_plan_fan_info(const PaxPlan *plan, int *rows_per_tile, int *warps, double *mean_run);
 /* self-check of the FAN kernel: 1 if any launch so far met a z window wider than its 32 lanes (the
  * row tile is derived so that this cannot happen); synchronises the device */

@@ -21,50 +21,54 @@
 // per stretch instead of one trilinear sample per step.  The sums are exactly TIGRE's Riemann sum
 // re-associated; only fp32 rounding differs (measured ~1e-7 relative L2 against the float64 oracle).
 //
-// Kernel shape (sm_100a, no tensor cores: this is a gather plus prefix sums).  A CTA owns one angle,
-// UC adjacent detector columns and a tile of `fan_rows` rows.  Per column and per run of equal n it
-// walks the chord in chunks of NW*B steps:
-//   phase 0  every thread prepares one step: in-plane cell offset and the four bilinear weights
+// Kernel shape (sm_100a, no tensor cores: this is a gather plus prefix sums).  Every WARP works on
+// its own detector column (one angle, one u, a tile of rows) with its own tables in shared memory;
+// there is no CTA-wide barrier, so the gather-heavy and the table-heavy phases of different warps
+// overlap on an SM.  Per run of equal n the warp cuts the rows into pieces whose z extent fits its
+// lanes, and walks the chord in chunks of G*8 steps:
+//   phase 0  a lane prepares one or two steps: in-plane cell offset and the four bilinear weights
 //            (positions from double, so nothing accumulates along the ray);
-//   phase 1  warp w owns B consecutive steps, lane l owns slice kA_w + l of the block's z window
-//            (the resident volume is z-fastest, so the four corner loads of a step are four
-//            coalesced 128-byte rows); it accumulates P and Q down the block and writes them to
-//            shared memory;
-//   phase 2  thread r owns detector row r of the tile and adds up its stretches from the tables.
-// The z window of a block (rows of the run x B steps) must fit the 32 lanes; pax_fan_configure
-// derives the row tile from the geometry so that it always does.
+//   phase 1  the warp advances G streams of 8 consecutive steps at once; a lane owns one stream and
+//            four consecutive slices of the chunk's z window (the resident volume is z-fastest, so a
+//            corner of a step is one 16-byte load per lane), accumulates P and Q down its stream and
+//            writes them to the table; a shuffle scan over the streams gives each its carry;
+//   phase 2  a lane owns up to RPL detector rows of the piece and adds up their stretches from the
+//            table (+ carry).
+// The z window of a chunk (rows of the piece x its steps) must fit the 4*LQ slices the lanes of a
+// stream cover; pax_fan_configure derives the piece size from the geometry so that it always does.
 #include <climits>
 #include <cmath>
 #include <cstdlib>
 
 #include "pax_internal.h"
 
-#define FAN_LQ 8           // lanes (z quads) per step: a chunk's z window is <= 32 slices
-#define FAN_W (4 * FAN_LQ)
-#define FAN_G (32 / FAN_LQ) // streams (runs of consecutive steps) a warp advances at once
-#define FAN_B 8            // steps per stream
-#define FAN_TS (FAN_W + 2) // table row stride in float2 (rows stay 16-byte aligned)
-#define FAN_UC 8           // detector columns per CTA (one 32-byte sector of every output row)
+#define FAN_B 8             // steps per stream
+#define FAN_NW 8            // warps per CTA (independent; the CTA only groups adjacent columns for L1)
+#define FAN_MAXTILE 1024    // detector rows one warp walks (run-start mask words below)
 
-template <int NW>
-struct FanSmem {
-    static constexpr int R = NW * 32;                  // threads; rows per tile <= R
-    static constexpr int NS = NW * FAN_G;              // streams per chunk
-    static constexpr int C = NS * FAN_B;               // steps per chunk
-    static constexpr int TROWS = C + NS;               // one spare row per stream (bank skew)
-    float2 T[TROWS * FAN_TS];                          // running (P,Q) per (step, slice), stream-local
-    float2 carry[NS * FAN_TS];                         // (P,Q) of all earlier streams of the chunk
-    float2 gsum[NW * FAN_W];                           // per-warp totals, input of the carry scan
-    float4 w[C + NS];                                  // bilinear weights per step (stream-padded)
-    int off[C + NS];                                   // in-plane cell offset per step
-    int n[R];
-    unsigned starts[NW];                               // bit r of word w: row 32w+r starts a run of equal n
-    int red[2];
+template <int LQ>
+struct FanCfg {
+    static constexpr int W = 4 * LQ;            // slices of a z window
+    static constexpr int G = 32 / LQ;           // streams a warp advances at once
+    static constexpr int CW = G * FAN_B;        // steps per chunk
+    static constexpr int TS = W + 2;            // table row stride in float2 (rows stay 16-byte aligned)
+    static constexpr int TROWS = CW + G;        // one spare row per stream (bank skew)
+};
+
+template <int LQ>
+struct __align__(16) FanWarpSmem {
+    using Cfg = FanCfg<LQ>;
+    float2 T[Cfg::TROWS * Cfg::TS];             // stream-local running (P,Q) per (step, slice)
+    float2 carry[Cfg::G * Cfg::TS];             // (P,Q) of all earlier streams of the chunk
+    float4 w[Cfg::TROWS];                       // bilinear weights per step (stream-padded)
+    int off[Cfg::TROWS];                        // in-plane cell offset per step
+    unsigned starts[FAN_MAXTILE / 32];          // bit r of word w: row 32w+r starts a run of equal n
 };
 
 // first row after `cur` that starts a new run (or nRows)
-__device__ __forceinline__ int fan_next_start(const unsigned *starts, int cur, int nRows, int nw)
+__device__ __forceinline__ int fan_next_start(const unsigned *starts, int cur, int nRows)
 {
+    const int nw = (nRows + 31) >> 5;
     int w = (cur + 1) >> 5;
     if (w >= nw) return nRows;
     unsigned bits = starts[w] & (0xffffffffu << ((cur + 1) & 31));
@@ -91,107 +95,114 @@ __device__ __forceinline__ void fan_slab(double s, double d, double lo, double h
 
 __device__ __forceinline__ float4 fan_ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
-// inclusive running (P,Q) of chunk-local step i (i >= 0) at table column c and c+1
+// inclusive running (P,Q) of chunk-local step i (i >= 0) at table columns c and c+1
+template <int LQ>
 __device__ __forceinline__ void fan_lookup(const float2 *T, const float2 *carry, int i, int c, float2 &lo,
                                            float2 &hi)
 {
+    constexpr int TS = FanCfg<LQ>::TS;
     const int s = i >> 3;                              // FAN_B == 8
-    const float2 *t = T + (i + s) * FAN_TS + c;
-    const float2 *k = carry + s * FAN_TS + c;
+    const float2 *t = T + (i + s) * TS + c;
+    const float2 *k = carry + s * TS + c;
     const float2 t0 = t[0], t1 = t[1], k0 = k[0], k1 = k[1];
     lo = make_float2(t0.x + k0.x, t0.y + k0.y);
     hi = make_float2(t1.x + k1.x, t1.y + k1.y);
 }
 
-template <int NW, int MODE>
-__global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
+template <int LQ, int RPL, int MODE>
+__global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
 {
-    using SM = FanSmem<NW>;
-    constexpr int R = SM::R, C = SM::C, NS = SM::NS, B = FAN_B, TS = FAN_TS, W = FAN_W;
+    using Cfg = FanCfg<LQ>;
+    constexpr int W = Cfg::W, G = Cfg::G, CW = Cfg::CW, TS = Cfg::TS, B = FAN_B;
     static_assert(FAN_B == 8, "fan_lookup assumes 8 steps per stream");
     extern __shared__ __align__(16) unsigned char fan_smem_raw[];
-    SM &sm = *reinterpret_cast<SM *>(fan_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FanWarpSmem<LQ> &sm = reinterpret_cast<FanWarpSmem<LQ> *>(fan_smem_raw)[warp];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = blockIdx.x * FAN_NW + warp;
+    if (u >= a.nu) return;                                        // warps are independent: no barriers below
     const int ia = blockIdx.y;
     const int V0 = blockIdx.z * a.fan_rows;
     const int nRows = min(a.fan_rows, a.nv - V0);
-    const int ucn = min(FAN_UC, a.nu - (int)blockIdx.x * FAN_UC);
     const AngleDev &A = a.angles[a.first + ia];
     const double sx = A.sx, sy = A.sy, sz = A.sz;
-    const double dz = A.oz + (double)(V0 + tid) * A.vz - sz;      // this thread's row
     const double zlo = (double)a.loz, zhi = (double)a.hiz;
     const int kmin = (int)a.loz, kmax = (int)a.hiz;               // slices a sample can touch: [kmin, kmax]
     const float kminf = a.loz, kmaxf = a.hiz;
     const int sxs = a.nzp, sys = a.nxp * a.nzp;
-    // phase-1 role of this lane: stream g of the warp, z quad q of the window
-    const int g = lane / FAN_LQ, q = lane % FAN_LQ;
-    const int strm = warp * FAN_G + g;
+    const int g = lane / LQ, q = lane % LQ;                       // phase-1 role: stream g, z quad q
+    const double dx = A.ox + u * A.ux - sx, dy = A.oy + u * A.uy - sy;
+    const double dxy2 = dx * dx + dy * dy;
+    const double racc = 1.0 / a.acc;
     unsigned my_ns = 0;
     float r2 = 0.f, mymax = -INFINITY;
 
-#pragma unroll 1
-    for (int uc = 0; uc < ucn; ++uc) {
-        float sum = 0.f, steplen = 0.f;
-        const int u = blockIdx.x * FAN_UC + uc;
-        const double dx = A.ox + u * A.ux - sx, dy = A.oy + u * A.uy - sy;
-        const double dxy2 = dx * dx + dy * dy;
-        // TIGRE's lattice: n = ceil(|P-S| / accuracy), per row
-        sm.n[tid] = (tid < nRows) ? (int)ceil(sqrt(dxy2 + dz * dz) / a.acc) : -1;
-        __syncthreads();
-        {
-            const bool st = tid < nRows && (tid == 0 || sm.n[tid] != sm.n[tid - 1]);
-            const unsigned bal = __ballot_sync(0xffffffffu, st);
-            if (lane == 0) sm.starts[warp] = bal;
+    // ---- runs of rows with equal n = ceil(|P-S| / accuracy)  (TIGRE's lattice)
+    {
+        int last = -2;
+        for (int r0 = 0; r0 < nRows; r0 += 32) {
+            const bool in = r0 + lane < nRows;
+            const double dz = A.oz + (double)(V0 + r0 + lane) * A.vz - sz;
+            const int n = in ? (int)ceil(sqrt(dxy2 + dz * dz) * racc) : -1;
+            int prev = __shfl_up_sync(0xffffffffu, n, 1);
+            if (lane == 0) prev = last;
+            const unsigned m = __ballot_sync(0xffffffffu, in && n != prev);
+            if (lane == 0) sm.starts[r0 >> 5] = m;
+            last = __shfl_sync(0xffffffffu, n, 31);
         }
-        __syncthreads();
-        int cur = 0;
-        while (cur < nRows) {
-            // ---- the run of rows [cur, e) that share n (uniform over the CTA)
-            const int nrun = sm.n[cur];
-            const int e = fan_next_start(sm.starts, cur, nRows, NW);
-            const double rn = 1.0 / (double)nrun;
-            const double ddx = dx * rn, ddy = dy * rn;
-            double t0 = 0.0, t1 = (double)nrun;
-            bool hit = true;
-            fan_slab(sx, ddx, 0.0, (double)a.hix, t0, t1, hit);
-            fan_slab(sy, ddy, 0.0, (double)a.hiy, t0, t1, hit);
-            // ---- this thread's row: its own z clip
-            const bool mine = tid >= cur && tid < e;
-            const double ddz = dz * rn;
-            int i0 = 0, i1 = -1;
-            if (mine) {
-                double tz0 = t0, tz1 = t1;
-                bool hz = hit;
-                fan_slab(sz, ddz, zlo, zhi, tz0, tz1, hz);
-                if (hz && tz0 <= tz1) { i0 = (int)ceil(tz0); i1 = (int)floor(tz1); }
+        __syncwarp();
+    }
+
+    int cur = 0;
+    while (cur < nRows) {
+        // ---- the run of rows [cur, e) that share n (uniform over the warp)
+        const int e = fan_next_start(sm.starts, cur, nRows);
+        const double dzc = A.oz + (double)(V0 + cur) * A.vz - sz;
+        const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
+        const double rn = 1.0 / (double)nrun;
+        const double ddx = dx * rn, ddy = dy * rn;
+        double t0 = 0.0, t1 = (double)nrun;
+        bool hit = true;
+        fan_slab(sx, ddx, 0.0, (double)a.hix, t0, t1, hit);
+        fan_slab(sy, ddy, 0.0, (double)a.hiy, t0, t1, hit);
+        const int len = e - cur;
+        const int npieces = (len + a.fan_piece - 1) / a.fan_piece;
+        const int psz = (len + npieces - 1) / npieces;
+        for (int pa = cur; pa < e; pa += psz) {
+            const int pb = min(e, pa + psz);
+            // ---- this lane's rows of the piece: pa + lane + 32 m
+            double ddz[RPL];
+            int i0[RPL], i1[RPL];
+            float sum[RPL];
+            int I0 = INT_MAX, I1 = -1;
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                const int r = pa + lane + 32 * m;
+                ddz[m] = (A.oz + (double)(V0 + r) * A.vz - sz) * rn;
+                i0[m] = 0; i1[m] = -1; sum[m] = 0.f;
+                if (r < pb) {
+                    double tz0 = t0, tz1 = t1;
+                    bool hz = hit;
+                    fan_slab(sz, ddz[m], zlo, zhi, tz0, tz1, hz);
+                    if (hz && tz0 <= tz1) { i0[m] = (int)ceil(tz0); i1[m] = (int)floor(tz1); }
+                    if (i0[m] <= i1[m]) {
+                        I0 = min(I0, i0[m]); I1 = max(I1, i1[m]);
+                        my_ns += (unsigned)(i1[m] - i0[m] + 1);
+                    }
+                }
             }
-            const bool valid = i0 <= i1;
-            if (tid == 0) { sm.red[0] = INT_MAX; sm.red[1] = -1; }
-            __syncthreads();
-            {
-                const int lo = __reduce_min_sync(0xffffffffu, valid ? i0 : INT_MAX);
-                const int hi = __reduce_max_sync(0xffffffffu, valid ? i1 : -1);
-                if (lane == 0 && hi >= 0) { atomicMin(&sm.red[0], lo); atomicMax(&sm.red[1], hi); }
-            }
-            __syncthreads();
-            const int I0 = sm.red[0], I1 = sm.red[1];
-            if (valid) {
-                const double mx = ddx * a.dX, my = ddy * a.dY, mz = ddz * a.dZ;
-                steplen = (float)sqrt(mx * mx + my * my + mz * mz);
-                my_ns += (unsigned)(i1 - i0 + 1);
-            }
+            I0 = __reduce_min_sync(0xffffffffu, I0);
+            I1 = __reduce_max_sync(0xffffffffu, I1);
             if (I0 <= I1) {
-                // z slopes per step of the run's first and last row: the corners of every z window
-                const double dzA = (A.oz + (double)(V0 + cur) * A.vz - sz) * rn;
-                const double dzB = (A.oz + (double)(V0 + e - 1) * A.vz - sz) * rn;
-                const float fdz = (float)ddz;
-                const float inv = 1.f / fabsf(fdz);
+                // z slopes per step of the piece's first and last row: the corners of every z window
+                const double dzA = (A.oz + (double)(V0 + pa) * A.vz - sz) * rn;
+                const double dzB = (A.oz + (double)(V0 + pb - 1) * A.vz - sz) * rn;
 #pragma unroll 1
-                for (int c0 = I0; c0 <= I1; c0 += C) {
-                    const int nst = min(C, I1 - c0 + 1);          // steps of this chunk
-                    // ---- phase 0: every thread prepares steps (in-plane cell + bilinear weights)
-                    for (int t = tid; t < C; t += R) {
+                for (int c0 = I0; c0 <= I1; c0 += CW) {
+                    const int nst = min(CW, I1 - c0 + 1);         // steps of this chunk
+                    // ---- phase 0: in-plane cell and bilinear weights of every step
+#pragma unroll
+                    for (int t = lane; t < CW; t += 32) {
                         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
                         int off = 0;
                         if (t < nst) {
@@ -207,7 +218,7 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                         sm.w[t + (t >> 3)] = w;
                         sm.off[t + (t >> 3)] = off;
                     }
-                    // ---- z window of the chunk: all rows of the run x all its steps (uniform)
+                    // ---- z window of the chunk: all rows of the piece x all its steps (uniform)
                     int kA, nq;
                     {
                         const double ja = (double)c0, jb = (double)(c0 + nst - 1);
@@ -216,11 +227,11 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                         const double zmax = fmax(fmax(z0, z1), fmax(z2, z3));
                         kA = max(kmin, (int)floor(zmin - 1e-3)) & ~3;
                         const int kB = min(kmax, (int)floor(zmax + 1e-3) + 1);
-                        nq = (kB - kA + 4) >> 2;                  // quads in the window; <= FAN_LQ by the
-                        if (nq > FAN_LQ && tid == 0 && a.fault)   // row tile pax_fan_configure chose
+                        nq = (kB - kA + 4) >> 2;                  // quads in the window; <= LQ by the piece
+                        if (nq > LQ && lane == 0 && a.fault)      // size pax_fan_configure chose
                             atomicExch(a.fault, 1);
                     }
-                    __syncthreads();
+                    __syncwarp();
                     // ---- phase 1: stream-local running sums, four slices per lane
                     {
                         const bool on = q < nq;
@@ -228,12 +239,12 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                         float4 P = make_float4(0.f, 0.f, 0.f, 0.f), Q = P;
                         float4 c00 = P, c01 = P, c10 = P, c11 = P;
                         int poff = -1;
-                        const int i_first = strm * B;
-                        const float4 *wp = sm.w + i_first + strm;
-                        const int *op = sm.off + i_first + strm;
-                        float4 *Tw = reinterpret_cast<float4 *>(sm.T + (i_first + strm) * TS + 4 * q);
-                        float jf = (float)(i_first - C / 2);
-                        if (i_first < nst) {
+                        const int row0 = g * (B + 1);             // table row of the stream's first step
+                        const float4 *wp = sm.w + row0;
+                        const int *op = sm.off + row0;
+                        float4 *Tw = reinterpret_cast<float4 *>(sm.T + row0 * TS + 4 * q);
+                        float jf = (float)(g * B - CW / 2);
+                        if (g * B < nst) {
 #pragma unroll 2
                             for (int s = 0; s < B; ++s) {
                                 const float4 w = wp[s];
@@ -259,12 +270,10 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                                 }
                             }
                         }
-                        // stream totals -> warp totals (exclusive over the warp's streams = carry within warp)
-                        // lanes of stream g hold its totals for quad q; scan over g with shuffles
-                        float4 cP = make_float4(0.f, 0.f, 0.f, 0.f), cQ = cP;      // sum of earlier streams of this warp
-                        float4 tP = P, tQ = Q;                                     // running inclusive
+                        // carry of a stream = totals of the earlier streams: inclusive scan over g, minus own
+                        float4 tP = P, tQ = Q;
 #pragma unroll
-                        for (int d = FAN_LQ; d < 32; d <<= 1) {
+                        for (int d = LQ; d < 32; d <<= 1) {
                             float4 oP, oQ;
                             oP.x = __shfl_up_sync(0xffffffffu, tP.x, d); oP.y = __shfl_up_sync(0xffffffffu, tP.y, d);
                             oP.z = __shfl_up_sync(0xffffffffu, tP.z, d); oP.w = __shfl_up_sync(0xffffffffu, tP.w, d);
@@ -275,39 +284,22 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                                 tQ.x += oQ.x; tQ.y += oQ.y; tQ.z += oQ.z; tQ.w += oQ.w;
                             }
                         }
-                        cP = make_float4(tP.x - P.x, tP.y - P.y, tP.z - P.z, tP.w - P.w);
-                        cQ = make_float4(tQ.x - Q.x, tQ.y - Q.y, tQ.z - Q.z, tQ.w - Q.w);
-                        // park the in-warp carry; the cross-warp part is added after the barrier
-                        float4 *cw = reinterpret_cast<float4 *>(sm.carry + strm * TS + 4 * q);
-                        cw[0] = make_float4(cP.x, cQ.x, cP.y, cQ.y);
-                        cw[1] = make_float4(cP.z, cQ.z, cP.w, cQ.w);
-                        if (g == FAN_G - 1) {                      // last stream's inclusive total = warp total
-                            float4 *gw = reinterpret_cast<float4 *>(sm.gsum + warp * W + 4 * q);
-                            gw[0] = make_float4(tP.x, tQ.x, tP.y, tQ.y);
-                            gw[1] = make_float4(tP.z, tQ.z, tP.w, tQ.w);
-                        }
+                        float4 *cw = reinterpret_cast<float4 *>(sm.carry + g * TS + 4 * q);
+                        cw[0] = make_float4(tP.x - P.x, tQ.x - Q.x, tP.y - P.y, tQ.y - Q.y);
+                        cw[1] = make_float4(tP.z - P.z, tQ.z - Q.z, tP.w - P.w, tQ.w - Q.w);
                     }
-                    __syncthreads();
-                    // ---- carry across warps: thread (stream s, column c) adds the totals of earlier warps
-                    for (int t = tid; t < NS * W; t += R) {
-                        const int s = t / W, c = t % W;
-                        const int ws = s / FAN_G;
-                        float2 acc = sm.carry[s * TS + c];
-                        for (int w2 = 0; w2 < ws; ++w2) {
-                            const float2 o = sm.gsum[w2 * W + c];
-                            acc.x += o.x; acc.y += o.y;
-                        }
-                        sm.carry[s * TS + c] = acc;
-                    }
-                    __syncthreads();
-                    // ---- phase 2: one detector row per thread, one table look-up pair per stretch end
-                    if (valid) {
-                        const int lo = max(i0, c0) - c0, hi = min(i1, c0 + C - 1) - c0;   // chunk-local steps
+                    __syncwarp();
+                    // ---- phase 2: the lane's detector rows, one table look-up pair per stretch end
+#pragma unroll
+                    for (int m = 0; m < RPL; ++m) {
+                        const int lo = max(i0[m], c0) - c0, hi = min(i1[m], c0 + CW - 1) - c0;   // chunk-local
                         if (lo <= hi) {
-                            const float zc0 = (float)(sz + (double)c0 * ddz);
-                            const float jc = (float)(C / 2);
+                            const float fdz = (float)ddz[m];
+                            const float inv = 1.f / fabsf(fdz);
+                            const float zc0 = (float)(sz + (double)c0 * ddz[m]);
+                            const float jc = (float)(CW / 2);
+                            float acc = 0.f;
                             int j = lo;
-                            // running sums just before the first step
                             float zl = fmaf((float)j, fdz, zc0);
                             while (j <= hi) {
                                 // fp32 z may round onto the clip bounds the double range excluded: keep the
@@ -315,55 +307,59 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
                                 const float kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
                                 const float tt = zl - kf;
                                 // steps that stay in slice pair (k, k+1)
-                                int m;
-                                if (fdz > 0.f) m = (int)fminf(ceilf((1.f - tt) * inv), 1.0e4f) - 1;
-                                else if (fdz < 0.f) m = (int)fminf(floorf(tt * inv), 1.0e4f);
-                                else m = C;
-                                const int je = min(hi, j + max(m, 0));
+                                int ms;
+                                if (fdz > 0.f) ms = (int)fminf(ceilf((1.f - tt) * inv), 1.0e4f) - 1;
+                                else if (fdz < 0.f) ms = (int)fminf(floorf(tt * inv), 1.0e4f);
+                                else ms = CW;
+                                const int je = min(hi, j + max(ms, 0));
                                 int kk = (int)kf - kA;
                                 if (kk < 0 || kk > 4 * nq - 2) {               // cannot happen: see pax_fan_configure
                                     if (a.fault) atomicExch(a.fault, 2);
                                     kk = min(max(kk, 0), W - 2);
                                 }
                                 float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0, b1;
-                                if (j > 0) fan_lookup(sm.T, sm.carry, j - 1, kk, a0, a1);
-                                fan_lookup(sm.T, sm.carry, je, kk, b0, b1);
+                                if (j > 0) fan_lookup<LQ>(sm.T, sm.carry, j - 1, kk, a0, a1);
+                                fan_lookup<LQ>(sm.T, sm.carry, je, kk, b0, b1);
                                 const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
                                 const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
-                                const float alpha = fmaf(jc - (float)j, fdz, tt);      // t at index C/2
-                                sum += fmaf(fdz, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
+                                const float alpha = fmaf(jc - (float)j, fdz, tt);      // t at index CW/2
+                                acc += fmaf(fdz, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
                                 j = je + 1;
                                 zl = fmaf((float)j, fdz, zc0);
                             }
+                            sum[m] += acc;
                         }
                     }
-                    __syncthreads();
+                    __syncwarp();
                 }
-            } else {
-                __syncthreads();          // sm.red is re-armed by the next run
             }
-            cur = e;
-        }
-        // ---- epilogue of this column for this thread's row.  The eight columns of the CTA fill one
-        // 32-byte sector of the row between them; L2 merges the partial writes.
-        if (tid < nRows) {
-            const int v = V0 + tid;
-            const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
-            const float p0 = sum * steplen;
-            if (MODE == PAX_AX_PLAIN) {
-                float val = a.a0 * p0;
-                if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
-                if (a.accumulate) val += a.out[o];
-                a.out[o] = val;
-                mymax = fmaxf(mymax, val);
-            } else {
-                const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
-                const float w = L > a.wthr ? 1.f / L : 0.f;
-                const float r = __ldg(a.b + o) - p0;
-                r2 = fmaf(r, r, r2);
-                a.out[o] = w * r;
+            // ---- epilogue of the piece.  The eight warps of the CTA own eight adjacent columns and
+            // fill one 32-byte sector of every row between them; L2 merges the partial writes.
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                const int r = pa + lane + 32 * m;
+                if (r < pb) {
+                    const int v = V0 + r;
+                    const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
+                    const double mx = ddx * a.dX, my = ddy * a.dY, mz = ddz[m] * a.dZ;
+                    const float p0 = sum[m] * (float)sqrt(mx * mx + my * my + mz * mz);
+                    if (MODE == PAX_AX_PLAIN) {
+                        float val = a.a0 * p0;
+                        if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
+                        if (a.accumulate) val += a.out[o];
+                        a.out[o] = val;
+                        mymax = fmaxf(mymax, val);
+                    } else {
+                        const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
+                        const float w = L > a.wthr ? 1.f / L : 0.f;
+                        const float r_ = __ldg(a.b + o) - p0;
+                        r2 = fmaf(r_, r_, r2);
+                        a.out[o] = w * r_;
+                    }
+                }
             }
         }
+        cur = e;
     }
     if (a.nsamples) {
         const unsigned t = __reduce_add_sync(0xffffffffu, my_ns);
@@ -383,8 +379,21 @@ __global__ void __launch_bounds__(NW * 32) k_ax_fan(const AxArgs a)
 }
 
 // ------------------------------------------------------------------------------ host side
-// Row tile for which every block's z window (rows of a run x FAN_B steps) fits FAN_K slices, and
+// Piece size (rows) for which every chunk's z window fits the lanes, per kernel configuration, and
 // the mean length of the equal-n runs (what the sharing is worth).  All from the plan's geometry.
+template <int LQ>
+static int fan_piece_rows(const PaxGeo &g, double vz, double tau, double slope, int rpl)
+{
+    // window of a chunk <= rows*vz*tau (spread of the rows) + steps*slope (travel) + 2 (floor, +1)
+    //                      + 3 (alignment to a quad) + slack  must fit W slices
+    const double room = (double)FanCfg<LQ>::W - 5.3 - FanCfg<LQ>::CW * slope;
+    int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
+    return std::max(0, std::min(rows, std::min(32 * rpl, (int)g.nDetecV)));
+}
+
+#define FAN_RPL4 3
+#define FAN_RPL8 6
+
 int pax_fan_configure(PaxPlan *p)
 {
     const PaxGeo &g = p->geo;
@@ -401,27 +410,18 @@ int pax_fan_configure(PaxPlan *p)
         const double za = std::fabs(A.oz - A.sz), zb = std::fabs(A.oz + (g.nDetecV - 1) * A.vz - A.sz);
         slope = std::fmax(slope, std::fmax(za, zb) / nmin);
     }
-    // window of a chunk <= rows*vz*tau (spread of the rows) + steps*slope (travel) + 2 (floor, +1)
-    //                      + 3 (alignment to a quad) must fit FAN_W slices
-    p->fan_rows = 0;
-    p->fan_warps = 0;
-    const int nws[3] = {8, 6, 4};
-    const char *force = getenv("PAX_FAN_WARPS");               // tuning hook
-    for (int c = 0; c < 3; ++c) {
-        const int nw = nws[c], steps = nw * FAN_G * FAN_B;
-        if (force && atoi(force) != nw) continue;
-        const double room = (double)FAN_W - 5.3 - steps * slope;
-        int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
-        rows = std::min(rows, std::min(nw * 32, (int)g.nDetecV));
-        if (rows < 1) continue;
-        // equal tiles; prefer the configuration that keeps the most threads busy in phase 2
-        const int tiles = (g.nDetecV + rows - 1) / rows;
-        rows = (g.nDetecV + tiles - 1) / tiles;
-        if (p->fan_rows == 0 || rows * p->fan_warps > p->fan_rows * nw) {
-            p->fan_rows = rows;
-            p->fan_warps = nw;
-        }
-    }
+    const int p4 = fan_piece_rows<4>(g, vz, tau, slope, FAN_RPL4);
+    const int p8 = fan_piece_rows<8>(g, vz, tau, slope, FAN_RPL8);
+    // a W=32 chunk costs twice a W=16 chunk per step: take it when it carries more than twice the rows
+    const char *force = getenv("PAX_FAN_LQ");                  // tuning hook
+    int lq = (p8 > 2 * p4) ? 8 : 4;
+    if (force && (atoi(force) == 4 || atoi(force) == 8)) lq = atoi(force);
+    p->fan_lq = lq;
+    p->fan_piece = lq == 8 ? p8 : p4;
+    p->fan_warps = FAN_NW;
+    // rows one warp walks: whole columns when short, else equal tiles of <= 512 rows
+    const int tiles = (g.nDetecV + 511) / 512;
+    p->fan_rows = std::min(FAN_MAXTILE, (g.nDetecV + tiles - 1) / tiles);
     // mean run length of equal n over three columns of the first angle
     {
         const AngleDev &A = p->h_angles[0];
@@ -442,14 +442,14 @@ int pax_fan_configure(PaxPlan *p)
     return PAX_OK;
 }
 
-template <int NW, int MODE>
+template <int LQ, int RPL, int MODE>
 static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
 {
-    const size_t smem = sizeof(FanSmem<NW>);
-    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = sizeof(FanWarpSmem<LQ>) * FAN_NW;
+    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<LQ, RPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-    dim3 grid(pax_cdiv(a.nu, FAN_UC), count, pax_cdiv(a.nv, a.fan_rows));
-    k_ax_fan<NW, MODE><<<grid, NW * 32, smem, st>>>(a);
+    dim3 grid(pax_cdiv(a.nu, FAN_NW), count, pax_cdiv(a.nv, a.fan_rows));
+    k_ax_fan<LQ, RPL, MODE><<<grid, FAN_NW * 32, smem, st>>>(a);
     return PAX_OK;
 }
 
@@ -457,14 +457,15 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
 {
     AxArgs a = a0;
     a.fan_rows = p->fan_rows;
+    a.fan_piece = p->fan_piece;
     a.fault = p->d_fault;
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
-    PAX_REQUIRE(p->fan_rows >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
-                                  "(z window of a single detector row exceeds %d slices)", FAN_W);
+    PAX_REQUIRE(p->fan_piece >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
+                                   "(the z window of a single detector row exceeds its lanes)");
     const bool plain = mode == PAX_AX_PLAIN;
-    switch (p->fan_warps) {
-    case 4: return plain ? fan_launch<4, PAX_AX_PLAIN>(a, count, st) : fan_launch<4, PAX_AX_RESIDUAL>(a, count, st);
-    case 6: return plain ? fan_launch<6, PAX_AX_PLAIN>(a, count, st) : fan_launch<6, PAX_AX_RESIDUAL>(a, count, st);
-    default: return plain ? fan_launch<8, PAX_AX_PLAIN>(a, count, st) : fan_launch<8, PAX_AX_RESIDUAL>(a, count, st);
-    }
+    if (p->fan_lq == 8)
+        return plain ? fan_launch<8, FAN_RPL8, PAX_AX_PLAIN>(a, count, st)
+                     : fan_launch<8, FAN_RPL8, PAX_AX_RESIDUAL>(a, count, st);
+    return plain ? fan_launch<4, FAN_RPL4, PAX_AX_PLAIN>(a, count, st)
+                 : fan_launch<4, FAN_RPL4, PAX_AX_RESIDUAL>(a, count, st);
 }

@@ -37,8 +37,10 @@ struct PaxPlan {
     AngleDev *d_angles;
     std::vector<AngleDev> h_angles;
     int projector;              // PAX_PROJECTOR_* requested (AUTO resolves per call)
-    int fan_rows;               // ax_fan.cu row tile that keeps every z window within 32 levels (0: none)
-    int fan_warps;              // warps per CTA for that tile
+    int fan_rows;               // ax_fan.cu: detector rows one warp walks
+    int fan_piece;              // most rows whose z window fits the lanes of a stream (0: FAN does not fit)
+    int fan_lq;                 // lanes per step (4: 16-slice windows, 8: 32-slice windows)
+    int fan_warps;              // warps per CTA
     double fan_run;             // mean length (rows) of the equal-n runs of a detector column
     int *d_fault;               // device word the fan kernel raises if a z window overflowed
 };
@@ -67,7 +69,8 @@ struct AxArgs {
     float dX, dY, dZ;
     float a0, a1, c;
     float whx, why, whz, wthr;
-    int fan_rows;                 // ax_fan.cu: detector rows per CTA tile
+    int fan_rows;                 // ax_fan.cu: detector rows one warp walks
+    int fan_piece;                // ax_fan.cu: most rows that share one z window
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
     int *fault;                   // ax_fan.cu: set to 1 if a z window did not fit (never, by construction)
 };

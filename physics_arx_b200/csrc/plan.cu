@@ -107,7 +107,7 @@ extern "C" int pax_plan_set_projector(PaxPlan *p, int kind)
     PAX_REQUIRE(p, "pax_plan_set_projector: NULL plan");
     PAX_REQUIRE(kind == PAX_PROJECTOR_AUTO || kind == PAX_PROJECTOR_RAY || kind == PAX_PROJECTOR_FAN,
                 "pax_plan_set_projector: unknown projector %d", kind);
-    PAX_REQUIRE(kind != PAX_PROJECTOR_FAN || p->fan_rows >= 1,
+    PAX_REQUIRE(kind != PAX_PROJECTOR_FAN || p->fan_piece >= 1,
                 "pax_plan_set_projector: the fan-plane projector does not fit this geometry");
     p->projector = kind;
     return PAX_OK;
@@ -125,7 +125,7 @@ extern "C" int pax_plan_projector(const PaxPlan *p)
 extern "C" int pax_plan_fan_info(const PaxPlan *p, int *rows_per_tile, int *warps, double *mean_run)
 {
     PAX_REQUIRE(p, "pax_plan_fan_info: NULL plan");
-    if (rows_per_tile) *rows_per_tile = p->fan_rows;
+    if (rows_per_tile) *rows_per_tile = p->fan_piece;
     if (warps) *warps = p->fan_warps;
     if (mean_run) *mean_run = p->fan_run;
     return PAX_OK;
