@@ -60,6 +60,7 @@ struct __align__(16) FanWarpSmem {
     using Cfg = FanCfg<LQ>;
     float2 T[Cfg::TROWS * Cfg::TS];             // stream-local running (P,Q) per (step, slice)
     float2 carry[Cfg::G * Cfg::TS];             // (P,Q) of all earlier streams of the chunk
+    float2 total[Cfg::TS];                      // (P,Q) of the whole chunk
     float4 w[Cfg::TROWS];                       // bilinear weights per step (stream-padded)
     int off[Cfg::TROWS];                        // in-plane cell offset per step
     unsigned starts[FAN_MAXTILE / 32];          // bit r of word w: row 32w+r starts a run of equal n
@@ -93,6 +94,20 @@ __device__ __forceinline__ void fan_slab(double s, double d, double lo, double h
     }
 }
 
+__device__ __forceinline__ void fan_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// predicated 16-byte read-only load: v keeps its value when `take` is false (no branch, so the load
+// can be issued a step ahead of its use)
+__device__ __forceinline__ void fan_ld4_if(float4 &v, const float *p, bool take)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                 : "r"((int)take), "l"(p));
+}
+__device__ __forceinline__ void fan_sel4(float4 &c, const float4 &n, bool take)
+{
+    c.x = take ? n.x : c.x; c.y = take ? n.y : c.y; c.z = take ? n.z : c.z; c.w = take ? n.w : c.w;
+}
 __device__ __forceinline__ float4 fan_ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 // inclusive running (P,Q) of chunk-local step i (i >= 0) at table columns c and c+1
@@ -130,6 +145,8 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
     const int kmin = (int)a.loz, kmax = (int)a.hiz;               // slices a sample can touch: [kmin, kmax]
     const float kminf = a.loz, kmaxf = a.hiz;
     const int sxs = a.nzp, sys = a.nxp * a.nzp;
+    const int xmaxc = (int)a.hix - 1, ymaxc = (int)a.hiy - 1;    // last in-plane cell whose +1 neighbour exists
+    const float szf = (float)sz;
     const int g = lane / LQ, q = lane % LQ;                       // phase-1 role: stream g, z quad q
     const double dx = A.ox + u * A.ux - sx, dy = A.oy + u * A.uy - sy;
     const double dxy2 = dx * dx + dy * dy;
@@ -173,13 +190,15 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
             // ---- this lane's rows of the piece: pa + lane + 32 m
             double ddz[RPL];
             int i0[RPL], i1[RPL];
-            float sum[RPL];
+            float sum[RPL], fdz[RPL], inv[RPL];
             int I0 = INT_MAX, I1 = -1;
 #pragma unroll
             for (int m = 0; m < RPL; ++m) {
                 const int r = pa + lane + 32 * m;
                 ddz[m] = (A.oz + (double)(V0 + r) * A.vz - sz) * rn;
                 i0[m] = 0; i1[m] = -1; sum[m] = 0.f;
+                fdz[m] = (float)ddz[m];
+                inv[m] = 1.f / fabsf(fdz[m]);
                 if (r < pb) {
                     double tz0 = t0, tz1 = t1;
                     bool hz = hit;
@@ -195,42 +214,74 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
             I1 = __reduce_max_sync(0xffffffffu, I1);
             if (I0 <= I1) {
                 // z slopes per step of the piece's first and last row: the corners of every z window
-                const double dzA = (A.oz + (double)(V0 + pa) * A.vz - sz) * rn;
-                const double dzB = (A.oz + (double)(V0 + pb - 1) * A.vz - sz) * rn;
-#pragma unroll 1
-                for (int c0 = I0; c0 <= I1; c0 += CW) {
-                    const int nst = min(CW, I1 - c0 + 1);         // steps of this chunk
-                    // ---- phase 0: in-plane cell and bilinear weights of every step
+                const float fdzA = (float)((A.oz + (double)(V0 + pa) * A.vz - sz) * rn);
+                const float fdzB = (float)((A.oz + (double)(V0 + pb - 1) * A.vz - sz) * rn);
+                // phase 0 + z window of the chunk starting at step c0; also asks L1 for the chunk's
+                // corner columns, so that phase 1 (which runs after the previous chunk's phase 2) finds them
+                auto prep = [&](const int c0, int &kA, int &nq, int &nst) {
+                    nst = min(CW, I1 - c0 + 1);                   // steps of this chunk
+                    // ---- phase 0: in-plane cell and bilinear weights of every step.  The chunk origin is
+                    // split in double into an integer cell and a fraction; steps add t*d to the fraction in
+                    // fp32 (|t| < CW), so a position is good to ~2e-6 voxels and nothing accumulates.
+                    {
+                        const double ex = sx + (double)c0 * ddx, ey = sy + (double)c0 * ddy;
+                        const double exi = floor(ex), eyi = floor(ey);
+                        const float exf = (float)(ex - exi), eyf = (float)(ey - eyi);
+                        const int exc = (int)exi, eyc = (int)eyi;
+                        const float fddx = (float)ddx, fddy = (float)ddy;
 #pragma unroll
-                    for (int t = lane; t < CW; t += 32) {
-                        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                        int off = 0;
-                        if (t < nst) {
-                            const double j = (double)(c0 + t);
-                            const float qx = (float)(sx + j * ddx), qy = (float)(sy + j * ddy);
-                            const float cx = fminf(fmaxf(floorf(qx), 0.f), a.hix - 1.f);
-                            const float cy = fminf(fmaxf(floorf(qy), 0.f), a.hiy - 1.f);
-                            const float fx = fminf(fmaxf(qx - cx, 0.f), 1.f), fy = fminf(fmaxf(qy - cy, 0.f), 1.f);
-                            off = ((int)cy * a.nxp + (int)cx) * a.nzp;
-                            const float gx = 1.f - fx, gy = 1.f - fy;
-                            w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
+                        for (int t = lane; t < CW; t += 32) {
+                            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                            int off = 0;
+                            if (t < nst) {
+                                const float px = fmaf((float)t, fddx, exf), py = fmaf((float)t, fddy, eyf);
+                                const float flx = floorf(px), fly = floorf(py);
+                                const int cx = min(max(exc + (int)flx, 0), xmaxc);
+                                const int cy = min(max(eyc + (int)fly, 0), ymaxc);
+                                // fraction against the CLAMPED cell: a sample the double clip admitted may sit
+                                // an ulp outside in fp32, and must then weigh the rim, not the next column
+                                const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
+                                const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
+                                off = (cy * a.nxp + cx) * a.nzp;
+                                const float gx = 1.f - fx, gy = 1.f - fy;
+                                w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
+                            }
+                            sm.w[t + (t >> 3)] = w;
+                            sm.off[t + (t >> 3)] = off;
                         }
-                        sm.w[t + (t >> 3)] = w;
-                        sm.off[t + (t >> 3)] = off;
                     }
                     // ---- z window of the chunk: all rows of the piece x all its steps (uniform)
-                    int kA, nq;
                     {
-                        const double ja = (double)c0, jb = (double)(c0 + nst - 1);
-                        const double z0 = sz + ja * dzA, z1 = sz + ja * dzB, z2 = sz + jb * dzA, z3 = sz + jb * dzB;
-                        const double zmin = fmin(fmin(z0, z1), fmin(z2, z3));
-                        const double zmax = fmax(fmax(z0, z1), fmax(z2, z3));
-                        kA = max(kmin, (int)floor(zmin - 1e-3)) & ~3;
-                        const int kB = min(kmax, (int)floor(zmax + 1e-3) + 1);
+                        const float ja = (float)c0, jb = (float)(c0 + nst - 1);
+                        const float z0 = fmaf(ja, fdzA, szf), z1 = fmaf(ja, fdzB, szf);
+                        const float z2 = fmaf(jb, fdzA, szf), z3 = fmaf(jb, fdzB, szf);
+                        const float zmin = fminf(fminf(z0, z1), fminf(z2, z3));
+                        const float zmax = fmaxf(fmaxf(z0, z1), fmaxf(z2, z3));
+                        kA = max(kmin, (int)floorf(zmin - 2e-3f)) & ~3;
+                        const int kB = min(kmax, (int)floorf(zmax + 2e-3f) + 1);
                         nq = (kB - kA + 4) >> 2;                  // quads in the window; <= LQ by the piece
                         if (nq > LQ && lane == 0 && a.fault)      // size pax_fan_configure chose
                             atomicExch(a.fault, 1);
                     }
+                    if (a.fan_prefetch && nq > 0) {
+                        const char *vb = reinterpret_cast<const char *>(a.vol0 + kA);
+                        const int span = 16 * nq - 4;             // last byte offset of the window, floats*4
+#pragma unroll
+                        for (int t = lane; t < CW; t += 32) {
+                            if (t < nst) {
+                                const char *p = vb + (size_t)sm.off[t + (t >> 3)] * 4;
+                                fan_prefetch_l1(p); fan_prefetch_l1(p + span);
+                                fan_prefetch_l1(p + sxs * 4); fan_prefetch_l1(p + sxs * 4 + span);
+                                fan_prefetch_l1(p + sys * 4); fan_prefetch_l1(p + sys * 4 + span);
+                                fan_prefetch_l1(p + (sys + sxs) * 4); fan_prefetch_l1(p + (sys + sxs) * 4 + span);
+                            }
+                        }
+                    }
+                };
+                int kA, nq, nst;
+                prep(I0, kA, nq, nst);
+#pragma unroll 1
+                for (int c0 = I0; c0 <= I1; c0 += CW) {
                     __syncwarp();
                     // ---- phase 1: stream-local running sums, four slices per lane
                     {
@@ -238,23 +289,31 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
                         const float *__restrict__ base = a.vol0 + kA + 4 * q;
                         float4 P = make_float4(0.f, 0.f, 0.f, 0.f), Q = P;
                         float4 c00 = P, c01 = P, c10 = P, c11 = P;
-                        int poff = -1;
                         const int row0 = g * (B + 1);             // table row of the stream's first step
                         const float4 *wp = sm.w + row0;
                         const int *op = sm.off + row0;
                         float4 *Tw = reinterpret_cast<float4 *>(sm.T + row0 * TS + 4 * q);
                         float jf = (float)(g * B - CW / 2);
                         if (g * B < nst) {
-#pragma unroll 2
+                            // Software pipeline: the corner columns of step s+1 are requested before step s
+                            // is computed (predicated loads into a second register set, moved over when the
+                            // cell really changes), so a step of arithmetic covers the L2 latency.
+                            const float *b00 = base, *b01 = base + sxs, *b10 = base + sys, *b11 = base + sys + sxs;
+                            int off = op[0];
+                            fan_ld4_if(c00, b00 + off, on); fan_ld4_if(c01, b01 + off, on);
+                            fan_ld4_if(c10, b10 + off, on); fan_ld4_if(c11, b11 + off, on);
+                            float4 n00 = c00, n01 = c01, n10 = c10, n11 = c11;
+#pragma unroll
                             for (int s = 0; s < B; ++s) {
-                                const float4 w = wp[s];
-                                const int off = op[s];
-                                if (on && off != poff) {
-                                    const float *p = base + off;
-                                    c00 = fan_ld4(p); c01 = fan_ld4(p + sxs);
-                                    c10 = fan_ld4(p + sys); c11 = fan_ld4(p + sys + sxs);
+                                bool chg = false;
+                                int offn = off;
+                                if (s + 1 < B) {
+                                    offn = op[s + 1];
+                                    chg = on && offn != off;
+                                    fan_ld4_if(n00, b00 + offn, chg); fan_ld4_if(n01, b01 + offn, chg);
+                                    fan_ld4_if(n10, b10 + offn, chg); fan_ld4_if(n11, b11 + offn, chg);
                                 }
-                                poff = off;
+                                const float4 w = wp[s];
                                 float4 v;
                                 v.x = fmaf(w.w, c11.x, fmaf(w.z, c10.x, fmaf(w.y, c01.x, w.x * c00.x)));
                                 v.y = fmaf(w.w, c11.y, fmaf(w.z, c10.y, fmaf(w.y, c01.y, w.x * c00.y)));
@@ -267,6 +326,11 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
                                 if (on) {
                                     Tw[s * (TS / 2)] = make_float4(P.x, Q.x, P.y, Q.y);
                                     Tw[s * (TS / 2) + 1] = make_float4(P.z, Q.z, P.w, Q.w);
+                                }
+                                if (s + 1 < B) {
+                                    fan_sel4(c00, n00, chg); fan_sel4(c01, n01, chg);
+                                    fan_sel4(c10, n10, chg); fan_sel4(c11, n11, chg);
+                                    off = offn;
                                 }
                             }
                         }
@@ -287,50 +351,70 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
                         float4 *cw = reinterpret_cast<float4 *>(sm.carry + g * TS + 4 * q);
                         cw[0] = make_float4(tP.x - P.x, tQ.x - Q.x, tP.y - P.y, tQ.y - Q.y);
                         cw[1] = make_float4(tP.z - P.z, tQ.z - Q.z, tP.w - P.w, tQ.w - Q.w);
+                        if (g == G - 1) {                           // inclusive total of the last stream = chunk total
+                            float4 *tw = reinterpret_cast<float4 *>(sm.total + 4 * q);
+                            tw[0] = make_float4(tP.x, tQ.x, tP.y, tQ.y);
+                            tw[1] = make_float4(tP.z, tQ.z, tP.w, tQ.w);
+                        }
                     }
                     __syncwarp();
+                    // ---- the next chunk's phase 0 (w/off are free again) and its L1 prefetch, hidden
+                    // behind this chunk's phase 2
+                    int kA2 = 0, nq2 = 0, nst2 = 0;
+                    if (c0 + CW <= I1) prep(c0 + CW, kA2, nq2, nst2);
                     // ---- phase 2: the lane's detector rows, one table look-up pair per stretch end
 #pragma unroll
                     for (int m = 0; m < RPL; ++m) {
                         const int lo = max(i0[m], c0) - c0, hi = min(i1[m], c0 + CW - 1) - c0;   // chunk-local
                         if (lo <= hi) {
-                            const float fdz = (float)ddz[m];
-                            const float inv = 1.f / fabsf(fdz);
+                            const float dzf = fdz[m];
                             const float zc0 = (float)(sz + (double)c0 * ddz[m]);
                             const float jc = (float)(CW / 2);
-                            float acc = 0.f;
-                            int j = lo;
-                            float zl = fmaf((float)j, fdz, zc0);
-                            while (j <= hi) {
-                                // fp32 z may round onto the clip bounds the double range excluded: keep the
-                                // slice pair inside [kmin, kmax] (tt then extrapolates by an ulp)
-                                const float kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
-                                const float tt = zl - kf;
-                                // steps that stay in slice pair (k, k+1)
-                                int ms;
-                                if (fdz > 0.f) ms = (int)fminf(ceilf((1.f - tt) * inv), 1.0e4f) - 1;
-                                else if (fdz < 0.f) ms = (int)fminf(floorf(tt * inv), 1.0e4f);
-                                else ms = CW;
-                                const int je = min(hi, j + max(ms, 0));
-                                int kk = (int)kf - kA;
-                                if (kk < 0 || kk > 4 * nq - 2) {               // cannot happen: see pax_fan_configure
-                                    if (a.fault) atomicExch(a.fault, 2);
-                                    kk = min(max(kk, 0), W - 2);
+                            float zl = fmaf((float)lo, dzf, zc0);
+                            const float zh = fmaf((float)hi, dzf, zc0);
+                            // fp32 z may round onto the clip bounds the double range excluded: keep the
+                            // slice pair inside [kmin, kmax] (tt then extrapolates by an ulp)
+                            float kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
+                            float acc;
+                            if (lo == 0 && hi == nst - 1 && floorf(zh) == kf) {
+                                // the row spans the whole chunk inside one slice pair: the chunk totals
+                                const int kk = min(max((int)kf - kA, 0), W - 2);
+                                const float2 b0 = sm.total[kk], b1 = sm.total[kk + 1];
+                                const float alpha = fmaf(jc, dzf, zl - kf);            // lo == 0
+                                acc = fmaf(dzf, b1.y - b0.y, fmaf(alpha, b1.x - b0.x, b0.x));
+                            } else {
+                                acc = 0.f;
+                                const float rinv = inv[m];
+                                int j = lo;
+                                while (j <= hi) {
+                                    const float tt = zl - kf;
+                                    // steps that stay in slice pair (k, k+1)
+                                    int ms;
+                                    if (dzf > 0.f) ms = (int)fminf(ceilf((1.f - tt) * rinv), 1.0e4f) - 1;
+                                    else if (dzf < 0.f) ms = (int)fminf(floorf(tt * rinv), 1.0e4f);
+                                    else ms = CW;
+                                    const int je = min(hi, j + max(ms, 0));
+                                    int kk = (int)kf - kA;
+                                    if (kk < 0 || kk > 4 * nq - 2) {           // cannot happen: see pax_fan_configure
+                                        if (a.fault) atomicExch(a.fault, 2);
+                                        kk = min(max(kk, 0), W - 2);
+                                    }
+                                    float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0, b1;
+                                    if (j > 0) fan_lookup<LQ>(sm.T, sm.carry, j - 1, kk, a0, a1);
+                                    fan_lookup<LQ>(sm.T, sm.carry, je, kk, b0, b1);
+                                    const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
+                                    const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
+                                    const float alpha = fmaf(jc - (float)j, dzf, tt);  // t at index CW/2
+                                    acc += fmaf(dzf, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
+                                    j = je + 1;
+                                    zl = fmaf((float)j, dzf, zc0);
+                                    kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
                                 }
-                                float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0, b1;
-                                if (j > 0) fan_lookup<LQ>(sm.T, sm.carry, j - 1, kk, a0, a1);
-                                fan_lookup<LQ>(sm.T, sm.carry, je, kk, b0, b1);
-                                const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
-                                const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
-                                const float alpha = fmaf(jc - (float)j, fdz, tt);      // t at index CW/2
-                                acc += fmaf(fdz, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
-                                j = je + 1;
-                                zl = fmaf((float)j, fdz, zc0);
                             }
                             sum[m] += acc;
                         }
                     }
-                    __syncwarp();
+                    kA = kA2; nq = nq2; nst = nst2;
                 }
             }
             // ---- epilogue of the piece.  The eight warps of the CTA own eight adjacent columns and
@@ -388,10 +472,11 @@ static int fan_piece_rows(const PaxGeo &g, double vz, double tau, double slope, 
     //                      + 3 (alignment to a quad) + slack  must fit W slices
     const double room = (double)FanCfg<LQ>::W - 5.3 - FanCfg<LQ>::CW * slope;
     int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
-    return std::max(0, std::min(rows, std::min(32 * rpl, (int)g.nDetecV)));
+    rows = std::max(0, std::min(rows, std::min(32 * rpl, (int)g.nDetecV)));
+    return rows >= 32 ? rows / 32 * 32 : rows;      // whole warps of rows: no idle lanes in phase 2
 }
 
-#define FAN_RPL4 3
+#define FAN_RPL4 2
 #define FAN_RPL8 6
 
 int pax_fan_configure(PaxPlan *p)
@@ -414,7 +499,7 @@ int pax_fan_configure(PaxPlan *p)
     const int p8 = fan_piece_rows<8>(g, vz, tau, slope, FAN_RPL8);
     // a W=32 chunk costs twice a W=16 chunk per step: take it when it carries more than twice the rows
     const char *force = getenv("PAX_FAN_LQ");                  // tuning hook
-    int lq = (p8 > 2 * p4) ? 8 : 4;
+    int lq = (p8 > 3 * p4) ? 8 : 4;                             // (measured at C2: 12.1 ms vs 10.0 ms)
     if (force && (atoi(force) == 4 || atoi(force) == 8)) lq = atoi(force);
     p->fan_lq = lq;
     p->fan_piece = lq == 8 ? p8 : p4;
@@ -459,6 +544,10 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     a.fan_rows = p->fan_rows;
     a.fan_piece = p->fan_piece;
     a.fault = p->d_fault;
+    {
+        const char *ev = getenv("PAX_FAN_PREFETCH");            // tuning hook
+        a.fan_prefetch = ev ? atoi(ev) : 0;      // measured at C2: 12.3 ms with, 10.2 ms without (L1 is too small)
+    }
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
     PAX_REQUIRE(p->fan_piece >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
                                    "(the z window of a single detector row exceeds its lanes)");

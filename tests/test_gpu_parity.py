@@ -284,6 +284,7 @@ def test_full_size_c2_projection_matches_oracle(oracle):
     vol = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
     ref = oracle.ax(vol, geo, angles)
     plan = Plan(geo, angles)
+    assert plan.projector == "fan"                     # what AUTO resolves to at C2
     res = plan.pack(torch.from_numpy(vol).cuda())
     for kind in ("fan", "ray"):
         plan.set_projector(kind)
