@@ -285,7 +285,7 @@ def main():
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
-                f"{cfg['name']}_ax_residual_bytes_per_launch")
+                f"{cfg['name']}_ax_residual_bytes_per_launch_{pipe.plan.projector}")
         except Exception:
             pass
         ax_share = float(sum(ax_ms)) / float(t[0].item()) if ax_ms else None
@@ -296,10 +296,13 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": describe(cfg, world, pipe.st.shard),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "k_ax<1,RESIDUAL,32>",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": ("k_ax_fan<4,2,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"
+                                    if pipe.plan.projector == "fan" else
+                                    "k_ax<1,RESIDUAL,32> (ray-march projector, csrc/ax.cu)"),
                          "peak_source": peak_src, "avg_launch_ms": avg_ms,
                          "alg_bytes_per_launch": alg_bytes, "share_of_step": ax_share,
-                         "note": "gather-bound (L1 wavefronts / issue slots), not HBM-bound: see "
+                         "note": "issue- and latency-bound gather + prefix sums, not HBM-bound: see "
                                  "ax_gsamples_per_s and profiles/"},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -62,7 +62,7 @@ struct __align__(16) FanWarpSmem {
     float2 carry[Cfg::G * Cfg::TS];             // (P,Q) of all earlier streams of the chunk
     float2 total[Cfg::TS];                      // (P,Q) of the whole chunk
     float4 w[Cfg::TROWS];                       // bilinear weights per step (stream-padded)
-    int off[Cfg::TROWS];                        // in-plane cell offset per step
+    unsigned off[Cfg::TROWS];                   // in-plane cell offset per step, bytes
     unsigned starts[FAN_MAXTILE / 32];          // bit r of word w: row 32w+r starts a run of equal n
 };
 
@@ -97,12 +97,25 @@ __device__ __forceinline__ void fan_slab(double s, double d, double lo, double h
 __device__ __forceinline__ void fan_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // predicated 16-byte read-only load: v keeps its value when `take` is false (no branch, so the load
 // can be issued a step ahead of its use)
-__device__ __forceinline__ void fan_ld4_if(float4 &v, const float *p, bool take)
+__device__ __forceinline__ void fan_ld4_if(float4 &v, const void *p, bool take)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
                  : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
                  : "r"((int)take), "l"(p));
+}
+// packed fp32x2 (sm_100 FMUL2/FFMA2): one issue slot for two slices
+__device__ __forceinline__ float2 fan_mul2(float w, float a, float b)
+{
+    return __fmul2_rn(make_float2(w, w), make_float2(a, b));
+}
+__device__ __forceinline__ float2 fan_fma2(float w, float a, float b, float2 acc)
+{
+    return __ffma2_rn(make_float2(w, w), make_float2(a, b), acc);
+}
+__device__ __forceinline__ float2 fan_shfl_up2(float2 v, int d)
+{
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
 }
 __device__ __forceinline__ void fan_sel4(float4 &c, const float4 &n, bool take)
 {
@@ -232,7 +245,7 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
 #pragma unroll
                         for (int t = lane; t < CW; t += 32) {
                             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                            int off = 0;
+                            unsigned off = 0;
                             if (t < nst) {
                                 const float px = fmaf((float)t, fddx, exf), py = fmaf((float)t, fddy, eyf);
                                 const float flx = floorf(px), fly = floorf(py);
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
                                 // an ulp outside in fp32, and must then weigh the rim, not the next column
                                 const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
                                 const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
-                                off = (cy * a.nxp + cx) * a.nzp;
+                                off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
                                 const float gx = 1.f - fx, gy = 1.f - fy;
                                 w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
                             }
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
 #pragma unroll
                         for (int t = lane; t < CW; t += 32) {
                             if (t < nst) {
-                                const char *p = vb + (size_t)sm.off[t + (t >> 3)] * 4;
+                                const char *p = vb + sm.off[t + (t >> 3)];
                                 fan_prefetch_l1(p); fan_prefetch_l1(p + span);
                                 fan_prefetch_l1(p + sxs * 4); fan_prefetch_l1(p + sxs * 4 + span);
                                 fan_prefetch_l1(p + sys * 4); fan_prefetch_l1(p + sys * 4 + span);
@@ -287,74 +300,74 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
                     {
                         const bool on = q < nq;
                         const float *__restrict__ base = a.vol0 + kA + 4 * q;
-                        float4 P = make_float4(0.f, 0.f, 0.f, 0.f), Q = P;
-                        float4 c00 = P, c01 = P, c10 = P, c11 = P;
+                        float2 pq0 = make_float2(0.f, 0.f), pq1 = pq0, pq2 = pq0, pq3 = pq0;   // running (P,Q) x 4 slices
+                        float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
                         const int row0 = g * (B + 1);             // table row of the stream's first step
                         const float4 *wp = sm.w + row0;
-                        const int *op = sm.off + row0;
+                        const unsigned *op = sm.off + row0;
                         float4 *Tw = reinterpret_cast<float4 *>(sm.T + row0 * TS + 4 * q);
                         float jf = (float)(g * B - CW / 2);
                         if (g * B < nst) {
-                            // Software pipeline: the corner columns of step s+1 are requested before step s
-                            // is computed (predicated loads into a second register set, moved over when the
-                            // cell really changes), so a step of arithmetic covers the L2 latency.
-                            const float *b00 = base, *b01 = base + sxs, *b10 = base + sys, *b11 = base + sys + sxs;
-                            int off = op[0];
-                            fan_ld4_if(c00, b00 + off, on); fan_ld4_if(c01, b01 + off, on);
-                            fan_ld4_if(c10, b10 + off, on); fan_ld4_if(c11, b11 + off, on);
-                            float4 n00 = c00, n01 = c01, n10 = c10, n11 = c11;
+                            // The corner columns of step s+1 are requested (predicated, no branch) right after
+                            // step s has consumed the registers, so the running-sum updates, the table stores
+                            // and the next step's address arithmetic cover part of the L2 latency.
+                            // byte offsets are unsigned 32-bit (pax_ax_fan_launch checks the volume is < 4 GB):
+                            // one 64-bit add per step, the other corners are uniform strides away
+                            const char *bb = reinterpret_cast<const char *>(base);
+                            const size_t dx4 = (size_t)sxs * 4, dy4 = (size_t)sys * 4;
+                            unsigned off = op[0];
+                            {
+                                const char *p00 = bb + off, *p10 = p00 + dy4;
+                                fan_ld4_if(c00, p00, on); fan_ld4_if(c01, p00 + dx4, on);
+                                fan_ld4_if(c10, p10, on); fan_ld4_if(c11, p10 + dx4, on);
+                            }
+                            float4 w = wp[0];
 #pragma unroll
                             for (int s = 0; s < B; ++s) {
-                                bool chg = false;
-                                int offn = off;
+                                unsigned offn = off;
+                                float4 wn = w;
+                                if (s + 1 < B) { offn = op[s + 1]; wn = wp[s + 1]; }
+                                const bool chg = on && offn != off;
+                                const char *p00 = bb + offn, *p10 = p00 + dy4;
+                                const char *p01 = p00 + dx4, *p11 = p10 + dx4;
+                                float2 v0 = fan_mul2(w.x, c00.x, c00.y), v1 = fan_mul2(w.x, c00.z, c00.w);
+                                v0 = fan_fma2(w.y, c01.x, c01.y, v0); v1 = fan_fma2(w.y, c01.z, c01.w, v1);
+                                v0 = fan_fma2(w.z, c10.x, c10.y, v0); v1 = fan_fma2(w.z, c10.z, c10.w, v1);
+                                v0 = fan_fma2(w.w, c11.x, c11.y, v0); v1 = fan_fma2(w.w, c11.z, c11.w, v1);
                                 if (s + 1 < B) {
-                                    offn = op[s + 1];
-                                    chg = on && offn != off;
-                                    fan_ld4_if(n00, b00 + offn, chg); fan_ld4_if(n01, b01 + offn, chg);
-                                    fan_ld4_if(n10, b10 + offn, chg); fan_ld4_if(n11, b11 + offn, chg);
+                                    fan_ld4_if(c00, p00, chg); fan_ld4_if(c01, p01, chg);
+                                    fan_ld4_if(c10, p10, chg); fan_ld4_if(c11, p11, chg);
                                 }
-                                const float4 w = wp[s];
-                                float4 v;
-                                v.x = fmaf(w.w, c11.x, fmaf(w.z, c10.x, fmaf(w.y, c01.x, w.x * c00.x)));
-                                v.y = fmaf(w.w, c11.y, fmaf(w.z, c10.y, fmaf(w.y, c01.y, w.x * c00.y)));
-                                v.z = fmaf(w.w, c11.z, fmaf(w.z, c10.z, fmaf(w.y, c01.z, w.x * c00.z)));
-                                v.w = fmaf(w.w, c11.w, fmaf(w.z, c10.w, fmaf(w.y, c01.w, w.x * c00.w)));
-                                P.x += v.x; P.y += v.y; P.z += v.z; P.w += v.w;
-                                Q.x = fmaf(jf, v.x, Q.x); Q.y = fmaf(jf, v.y, Q.y);
-                                Q.z = fmaf(jf, v.z, Q.z); Q.w = fmaf(jf, v.w, Q.w);
+                                pq0.x += v0.x; pq1.x += v0.y; pq2.x += v1.x; pq3.x += v1.y;
+                                pq0.y = fmaf(jf, v0.x, pq0.y); pq1.y = fmaf(jf, v0.y, pq1.y);
+                                pq2.y = fmaf(jf, v1.x, pq2.y); pq3.y = fmaf(jf, v1.y, pq3.y);
                                 jf += 1.f;
                                 if (on) {
-                                    Tw[s * (TS / 2)] = make_float4(P.x, Q.x, P.y, Q.y);
-                                    Tw[s * (TS / 2) + 1] = make_float4(P.z, Q.z, P.w, Q.w);
+                                    Tw[s * (TS / 2)] = make_float4(pq0.x, pq0.y, pq1.x, pq1.y);
+                                    Tw[s * (TS / 2) + 1] = make_float4(pq2.x, pq2.y, pq3.x, pq3.y);
                                 }
-                                if (s + 1 < B) {
-                                    fan_sel4(c00, n00, chg); fan_sel4(c01, n01, chg);
-                                    fan_sel4(c10, n10, chg); fan_sel4(c11, n11, chg);
-                                    off = offn;
-                                }
+                                off = offn;
+                                w = wn;
                             }
                         }
                         // carry of a stream = totals of the earlier streams: inclusive scan over g, minus own
-                        float4 tP = P, tQ = Q;
+                        float2 t0 = pq0, t1 = pq1, t2 = pq2, t3 = pq3;
 #pragma unroll
                         for (int d = LQ; d < 32; d <<= 1) {
-                            float4 oP, oQ;
-                            oP.x = __shfl_up_sync(0xffffffffu, tP.x, d); oP.y = __shfl_up_sync(0xffffffffu, tP.y, d);
-                            oP.z = __shfl_up_sync(0xffffffffu, tP.z, d); oP.w = __shfl_up_sync(0xffffffffu, tP.w, d);
-                            oQ.x = __shfl_up_sync(0xffffffffu, tQ.x, d); oQ.y = __shfl_up_sync(0xffffffffu, tQ.y, d);
-                            oQ.z = __shfl_up_sync(0xffffffffu, tQ.z, d); oQ.w = __shfl_up_sync(0xffffffffu, tQ.w, d);
+                            const float2 o0 = fan_shfl_up2(t0, d), o1 = fan_shfl_up2(t1, d);
+                            const float2 o2 = fan_shfl_up2(t2, d), o3 = fan_shfl_up2(t3, d);
                             if (lane >= d) {
-                                tP.x += oP.x; tP.y += oP.y; tP.z += oP.z; tP.w += oP.w;
-                                tQ.x += oQ.x; tQ.y += oQ.y; tQ.z += oQ.z; tQ.w += oQ.w;
+                                t0 = __fadd2_rn(t0, o0); t1 = __fadd2_rn(t1, o1);
+                                t2 = __fadd2_rn(t2, o2); t3 = __fadd2_rn(t3, o3);
                             }
                         }
                         float4 *cw = reinterpret_cast<float4 *>(sm.carry + g * TS + 4 * q);
-                        cw[0] = make_float4(tP.x - P.x, tQ.x - Q.x, tP.y - P.y, tQ.y - Q.y);
-                        cw[1] = make_float4(tP.z - P.z, tQ.z - Q.z, tP.w - P.w, tQ.w - Q.w);
+                        cw[0] = make_float4(t0.x - pq0.x, t0.y - pq0.y, t1.x - pq1.x, t1.y - pq1.y);
+                        cw[1] = make_float4(t2.x - pq2.x, t2.y - pq2.y, t3.x - pq3.x, t3.y - pq3.y);
                         if (g == G - 1) {                           // inclusive total of the last stream = chunk total
                             float4 *tw = reinterpret_cast<float4 *>(sm.total + 4 * q);
-                            tw[0] = make_float4(tP.x, tQ.x, tP.y, tQ.y);
-                            tw[1] = make_float4(tP.z, tQ.z, tP.w, tQ.w);
+                            tw[0] = make_float4(t0.x, t0.y, t1.x, t1.y);
+                            tw[1] = make_float4(t2.x, t2.y, t3.x, t3.y);
                         }
                     }
                     __syncwarp();
@@ -549,6 +562,7 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
         a.fan_prefetch = ev ? atoi(ev) : 0;      // measured at C2: 12.3 ms with, 10.2 ms without (L1 is too small)
     }
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
+    PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
     PAX_REQUIRE(p->fan_piece >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
                                    "(the z window of a single detector row exceeds its lanes)");
     const bool plain = mode == PAX_AX_PLAIN;
