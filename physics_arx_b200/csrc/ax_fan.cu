@@ -42,22 +42,24 @@
 
 #include "pax_internal.h"
 
-#define FAN_B 8             // steps per stream
 #define FAN_NW 8            // warps per CTA (independent; the CTA only groups adjacent columns for L1)
 #define FAN_MAXTILE 1024    // detector rows one warp walks (run-start mask words below)
 
-template <int LQ>
+// LQ lanes (z quads) per step, SB steps per stream
+template <int LQ, int SB>
 struct FanCfg {
     static constexpr int W = 4 * LQ;            // slices of a z window
     static constexpr int G = 32 / LQ;           // streams a warp advances at once
-    static constexpr int CW = G * FAN_B;        // steps per chunk
+    static constexpr int B = SB;
+    static constexpr int LOGB = SB == 16 ? 4 : 3;
+    static constexpr int CW = G * SB;           // steps per chunk
     static constexpr int TS = W + 2;            // table row stride in float2 (rows stay 16-byte aligned)
     static constexpr int TROWS = CW + G;        // one spare row per stream (bank skew)
 };
 
-template <int LQ>
+template <int LQ, int SB>
 struct __align__(16) FanWarpSmem {
-    using Cfg = FanCfg<LQ>;
+    using Cfg = FanCfg<LQ, SB>;
     float2 T[Cfg::TROWS * Cfg::TS];             // stream-local running (P,Q) per (step, slice)
     float2 carry[Cfg::G * Cfg::TS];             // (P,Q) of all earlier streams of the chunk
     float2 total[Cfg::TS];                      // (P,Q) of the whole chunk
@@ -124,12 +126,12 @@ __device__ __forceinline__ void fan_sel4(float4 &c, const float4 &n, bool take)
 __device__ __forceinline__ float4 fan_ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 // inclusive running (P,Q) of chunk-local step i (i >= 0) at table columns c and c+1
-template <int LQ>
+template <int LQ, int SB>
 __device__ __forceinline__ void fan_lookup(const float2 *T, const float2 *carry, int i, int c, float2 &lo,
                                            float2 &hi)
 {
-    constexpr int TS = FanCfg<LQ>::TS;
-    const int s = i >> 3;                              // FAN_B == 8
+    constexpr int TS = FanCfg<LQ, SB>::TS;
+    const int s = i >> FanCfg<LQ, SB>::LOGB;
     const float2 *t = T + (i + s) * TS + c;
     const float2 *k = carry + s * TS + c;
     const float2 t0 = t[0], t1 = t[1], k0 = k[0], k1 = k[1];
@@ -137,17 +139,17 @@ __device__ __forceinline__ void fan_lookup(const float2 *T, const float2 *carry,
     hi = make_float2(t1.x + k1.x, t1.y + k1.y);
 }
 
-template <int LQ, int RPL, int MODE>
-__global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
+template <int LQ, int SB, int RPL, int NWARPS, int MODE>
+__global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
 {
-    using Cfg = FanCfg<LQ>;
-    constexpr int W = Cfg::W, G = Cfg::G, CW = Cfg::CW, TS = Cfg::TS, B = FAN_B;
-    static_assert(FAN_B == 8, "fan_lookup assumes 8 steps per stream");
+    using Cfg = FanCfg<LQ, SB>;
+    constexpr int W = Cfg::W, G = Cfg::G, CW = Cfg::CW, TS = Cfg::TS, B = SB, LOGB = Cfg::LOGB;
+    static_assert(SB == 8 || SB == 16, "8 or 16 steps per stream");
     extern __shared__ __align__(16) unsigned char fan_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    FanWarpSmem<LQ> &sm = reinterpret_cast<FanWarpSmem<LQ> *>(fan_smem_raw)[warp];
+    FanWarpSmem<LQ, SB> &sm = reinterpret_cast<FanWarpSmem<LQ, SB> *>(fan_smem_raw)[warp];
 
-    const int u = blockIdx.x * FAN_NW + warp;
+    const int u = blockIdx.x * NWARPS + warp;
     if (u >= a.nu) return;                                        // warps are independent: no barriers below
     const int ia = blockIdx.y;
     const int V0 = blockIdx.z * a.fan_rows;
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
                                 const float gx = 1.f - fx, gy = 1.f - fy;
                                 w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
                             }
-                            sm.w[t + (t >> 3)] = w;
-                            sm.off[t + (t >> 3)] = off;
+                            sm.w[t + (t >> LOGB)] = w;
+                            sm.off[t + (t >> LOGB)] = off;
                         }
                     }
                     // ---- z window of the chunk: all rows of the piece x all its steps (uniform)
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
 #pragma unroll
                         for (int t = lane; t < CW; t += 32) {
                             if (t < nst) {
-                                const char *p = vb + sm.off[t + (t >> 3)];
+                                const char *p = vb + sm.off[t + (t >> LOGB)];
                                 fan_prefetch_l1(p); fan_prefetch_l1(p + span);
                                 fan_prefetch_l1(p + sxs * 4); fan_prefetch_l1(p + sxs * 4 + span);
                                 fan_prefetch_l1(p + sys * 4); fan_prefetch_l1(p + sys * 4 + span);
@@ -413,8 +415,8 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
                                         kk = min(max(kk, 0), W - 2);
                                     }
                                     float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0, b1;
-                                    if (j > 0) fan_lookup<LQ>(sm.T, sm.carry, j - 1, kk, a0, a1);
-                                    fan_lookup<LQ>(sm.T, sm.carry, je, kk, b0, b1);
+                                    if (j > 0) fan_lookup<LQ, SB>(sm.T, sm.carry, j - 1, kk, a0, a1);
+                                    fan_lookup<LQ, SB>(sm.T, sm.carry, je, kk, b0, b1);
                                     const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
                                     const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
                                     const float alpha = fmaf(jc - (float)j, dzf, tt);  // t at index CW/2
@@ -478,19 +480,20 @@ __global__ void __launch_bounds__(FAN_NW * 32) k_ax_fan(const AxArgs a)
 // ------------------------------------------------------------------------------ host side
 // Piece size (rows) for which every chunk's z window fits the lanes, per kernel configuration, and
 // the mean length of the equal-n runs (what the sharing is worth).  All from the plan's geometry.
-template <int LQ>
+template <int LQ, int SB>
 static int fan_piece_rows(const PaxGeo &g, double vz, double tau, double slope, int rpl)
 {
     // window of a chunk <= rows*vz*tau (spread of the rows) + steps*slope (travel) + 2 (floor, +1)
     //                      + 3 (alignment to a quad) + slack  must fit W slices
-    const double room = (double)FanCfg<LQ>::W - 5.3 - FanCfg<LQ>::CW * slope;
+    const double room = (double)FanCfg<LQ, SB>::W - 5.3 - FanCfg<LQ, SB>::CW * slope;
     int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
     rows = std::max(0, std::min(rows, std::min(32 * rpl, (int)g.nDetecV)));
     return rows >= 32 ? rows / 32 * 32 : rows;      // whole warps of rows: no idle lanes in phase 2
 }
 
 #define FAN_RPL4 2
-#define FAN_RPL8 6
+#define FAN_RPL8 4
+#define FAN_NW8 5            // W=32 tables are twice as large: five warps per CTA, two CTAs per SM
 
 int pax_fan_configure(PaxPlan *p)
 {
@@ -508,15 +511,15 @@ int pax_fan_configure(PaxPlan *p)
         const double za = std::fabs(A.oz - A.sz), zb = std::fabs(A.oz + (g.nDetecV - 1) * A.vz - A.sz);
         slope = std::fmax(slope, std::fmax(za, zb) / nmin);
     }
-    const int p4 = fan_piece_rows<4>(g, vz, tau, slope, FAN_RPL4);
-    const int p8 = fan_piece_rows<8>(g, vz, tau, slope, FAN_RPL8);
+    const int p4 = fan_piece_rows<4, 8>(g, vz, tau, slope, FAN_RPL4);
+    const int p8 = fan_piece_rows<8, 16>(g, vz, tau, slope, FAN_RPL8);
     // a W=32 chunk costs twice a W=16 chunk per step: take it when it carries more than twice the rows
     const char *force = getenv("PAX_FAN_LQ");                  // tuning hook
     int lq = (p8 > 3 * p4) ? 8 : 4;                             // (measured at C2: 12.1 ms vs 10.0 ms)
     if (force && (atoi(force) == 4 || atoi(force) == 8)) lq = atoi(force);
     p->fan_lq = lq;
     p->fan_piece = lq == 8 ? p8 : p4;
-    p->fan_warps = FAN_NW;
+    p->fan_warps = lq == 8 ? FAN_NW8 : FAN_NW;
     // rows one warp walks: whole columns when short, else equal tiles of <= 512 rows
     const int tiles = (g.nDetecV + 511) / 512;
     p->fan_rows = std::min(FAN_MAXTILE, (g.nDetecV + tiles - 1) / tiles);
@@ -540,14 +543,14 @@ int pax_fan_configure(PaxPlan *p)
     return PAX_OK;
 }
 
-template <int LQ, int RPL, int MODE>
+template <int LQ, int SB, int RPL, int NWARPS, int MODE>
 static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
 {
-    const size_t smem = sizeof(FanWarpSmem<LQ>) * FAN_NW;
-    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<LQ, RPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    dim3 grid(pax_cdiv(a.nu, FAN_NW), count, pax_cdiv(a.nv, a.fan_rows));
-    k_ax_fan<LQ, RPL, MODE><<<grid, FAN_NW * 32, smem, st>>>(a);
+    const size_t smem = sizeof(FanWarpSmem<LQ, SB>) * NWARPS;
+    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<LQ, SB, RPL, NWARPS, MODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(pax_cdiv(a.nu, NWARPS), count, pax_cdiv(a.nv, a.fan_rows));
+    k_ax_fan<LQ, SB, RPL, NWARPS, MODE><<<grid, NWARPS * 32, smem, st>>>(a);
     return PAX_OK;
 }
 
@@ -567,8 +570,8 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
                                    "(the z window of a single detector row exceeds its lanes)");
     const bool plain = mode == PAX_AX_PLAIN;
     if (p->fan_lq == 8)
-        return plain ? fan_launch<8, FAN_RPL8, PAX_AX_PLAIN>(a, count, st)
-                     : fan_launch<8, FAN_RPL8, PAX_AX_RESIDUAL>(a, count, st);
-    return plain ? fan_launch<4, FAN_RPL4, PAX_AX_PLAIN>(a, count, st)
-                 : fan_launch<4, FAN_RPL4, PAX_AX_RESIDUAL>(a, count, st);
+        return plain ? fan_launch<8, 16, FAN_RPL8, FAN_NW8, PAX_AX_PLAIN>(a, count, st)
+                     : fan_launch<8, 16, FAN_RPL8, FAN_NW8, PAX_AX_RESIDUAL>(a, count, st);
+    return plain ? fan_launch<4, 8, FAN_RPL4, FAN_NW, PAX_AX_PLAIN>(a, count, st)
+                 : fan_launch<4, 8, FAN_RPL4, FAN_NW, PAX_AX_RESIDUAL>(a, count, st);
 }
