@@ -43,7 +43,8 @@
 #include "pax_internal.h"
 
 #define FAN_NW 8            // warps per CTA (independent; the CTA only groups adjacent columns for L1)
-#define FAN_MAXTILE 1024    // detector rows one warp walks (run-start mask words below)
+#define FAN_GROUP 128       // most rows summed from one set of tables
+#define FAN_MAXTILE 256     // detector rows one warp walks (their sums and run-start masks live in smem)
 
 // LQ lanes (z quads) per step, SB steps per stream
 template <int LQ, int SB>
@@ -66,6 +67,7 @@ struct __align__(16) FanWarpSmem {
     float4 w[Cfg::TROWS];                       // bilinear weights per step (stream-padded)
     unsigned off[Cfg::TROWS];                   // in-plane cell offset per step, bytes
     unsigned starts[FAN_MAXTILE / 32];          // bit r of word w: row 32w+r starts a run of equal n
+    float rsum[FAN_MAXTILE];                    // running line integral of every row of the tile
 };
 
 // first row after `cur` that starts a new run (or nRows)
@@ -139,11 +141,99 @@ __device__ __forceinline__ void fan_lookup(const float2 *T, const float2 *carry,
     hi = make_float2(t1.x + k1.x, t1.y + k1.y);
 }
 
+// ---- phase 1 of a chunk: stream-local running sums of G, four slices per lane, into the table; then
+// the carries of the streams and the chunk totals.  kA = first slice of the window (multiple of 4),
+// nq = quads in it, nst = steps of the chunk.
+template <int LQ, int SB>
+__device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float *__restrict__ vol, int sxs,
+                                           int sys, int kA, int nq, int nst, int lane)
+{
+    using Cfg = FanCfg<LQ, SB>;
+    constexpr int G = Cfg::G, CW = Cfg::CW, TS = Cfg::TS, B = SB;
+    const int g = lane / LQ, q = lane % LQ;                       // stream g, z quad q
+        const bool on = q < nq;
+        const float *__restrict__ base = vol + kA + 4 * q;
+        float2 pq0 = make_float2(0.f, 0.f), pq1 = pq0, pq2 = pq0, pq3 = pq0;   // running (P,Q) x 4 slices
+        float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
+        const int row0 = g * (B + 1);             // table row of the stream's first step
+        const float4 *wp = sm.w + row0;
+        const unsigned *op = sm.off + row0;
+        float4 *Tw = reinterpret_cast<float4 *>(sm.T + row0 * TS + 4 * q);
+        float jf = (float)(g * B - CW / 2);
+        if (g * B < nst) {
+            // Two register sets of corner columns, one for the even and one for the odd steps: as soon
+            // as step s has consumed its set, the columns of step s+2 are requested into it (predicated:
+            // no load when the cell is the same), so a whole step of arithmetic covers the L2 latency
+            // and no register moves are needed.
+            // byte offsets are unsigned 32-bit (pax_ax_fan_launch checks the volume is < 4 GB):
+            // one 64-bit add per step, the other corners are uniform strides away
+            const char *bb = reinterpret_cast<const char *>(base);
+            const size_t dx4 = (size_t)sxs * 4, dy4 = (size_t)sys * 4;
+            float4 d00 = c00, d01 = c00, d10 = c00, d11 = c00;           // the odd steps' set
+            unsigned offE = op[0], offO = op[1];
+            {
+                const char *p00 = bb + offE, *p10 = p00 + dy4;
+                fan_ld4_if(c00, p00, on); fan_ld4_if(c01, p00 + dx4, on);
+                fan_ld4_if(c10, p10, on); fan_ld4_if(c11, p10 + dx4, on);
+                const char *q00 = bb + offO, *q10 = q00 + dy4;
+                fan_ld4_if(d00, q00, on); fan_ld4_if(d01, q00 + dx4, on);
+                fan_ld4_if(d10, q10, on); fan_ld4_if(d11, q10 + dx4, on);
+            }
+            auto step = [&](const int s, float4 &x00, float4 &x01, float4 &x10, float4 &x11, unsigned &offx) {
+                const float4 w = wp[s];
+                float2 v0 = fan_mul2(w.x, x00.x, x00.y), v1 = fan_mul2(w.x, x00.z, x00.w);
+                v0 = fan_fma2(w.y, x01.x, x01.y, v0); v1 = fan_fma2(w.y, x01.z, x01.w, v1);
+                v0 = fan_fma2(w.z, x10.x, x10.y, v0); v1 = fan_fma2(w.z, x10.z, x10.w, v1);
+                v0 = fan_fma2(w.w, x11.x, x11.y, v0); v1 = fan_fma2(w.w, x11.z, x11.w, v1);
+                if (s + 2 < B) {
+                    const unsigned offn = op[s + 2];
+                    const bool chg = on && offn != offx;
+                    const char *p00 = bb + offn, *p10 = p00 + dy4;
+                    fan_ld4_if(x00, p00, chg); fan_ld4_if(x01, p00 + dx4, chg);
+                    fan_ld4_if(x10, p10, chg); fan_ld4_if(x11, p10 + dx4, chg);
+                    offx = offn;
+                }
+                pq0.x += v0.x; pq1.x += v0.y; pq2.x += v1.x; pq3.x += v1.y;
+                pq0.y = fmaf(jf, v0.x, pq0.y); pq1.y = fmaf(jf, v0.y, pq1.y);
+                pq2.y = fmaf(jf, v1.x, pq2.y); pq3.y = fmaf(jf, v1.y, pq3.y);
+                jf += 1.f;
+                if (on) {
+                    Tw[s * (TS / 2)] = make_float4(pq0.x, pq0.y, pq1.x, pq1.y);
+                    Tw[s * (TS / 2) + 1] = make_float4(pq2.x, pq2.y, pq3.x, pq3.y);
+                }
+            };
+    #pragma unroll
+            for (int s = 0; s < B; s += 2) {
+                step(s, c00, c01, c10, c11, offE);
+                step(s + 1, d00, d01, d10, d11, offO);
+            }
+        }
+        // carry of a stream = totals of the earlier streams: inclusive scan over g, minus own
+        float2 t0 = pq0, t1 = pq1, t2 = pq2, t3 = pq3;
+    #pragma unroll
+        for (int d = LQ; d < 32; d <<= 1) {
+            const float2 o0 = fan_shfl_up2(t0, d), o1 = fan_shfl_up2(t1, d);
+            const float2 o2 = fan_shfl_up2(t2, d), o3 = fan_shfl_up2(t3, d);
+            if (lane >= d) {
+                t0 = __fadd2_rn(t0, o0); t1 = __fadd2_rn(t1, o1);
+                t2 = __fadd2_rn(t2, o2); t3 = __fadd2_rn(t3, o3);
+            }
+        }
+        float4 *cw = reinterpret_cast<float4 *>(sm.carry + g * TS + 4 * q);
+        cw[0] = make_float4(t0.x - pq0.x, t0.y - pq0.y, t1.x - pq1.x, t1.y - pq1.y);
+        cw[1] = make_float4(t2.x - pq2.x, t2.y - pq2.y, t3.x - pq3.x, t3.y - pq3.y);
+        if (g == G - 1) {                           // inclusive total of the last stream = chunk total
+            float4 *tw = reinterpret_cast<float4 *>(sm.total + 4 * q);
+            tw[0] = make_float4(t0.x, t0.y, t1.x, t1.y);
+            tw[1] = make_float4(t2.x, t2.y, t3.x, t3.y);
+        }
+}
+
 template <int LQ, int SB, int RPL, int NWARPS, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
 {
     using Cfg = FanCfg<LQ, SB>;
-    constexpr int W = Cfg::W, G = Cfg::G, CW = Cfg::CW, TS = Cfg::TS, B = SB, LOGB = Cfg::LOGB;
+    constexpr int W = Cfg::W, CW = Cfg::CW, LOGB = Cfg::LOGB;
     static_assert(SB == 8 || SB == 16, "8 or 16 steps per stream");
     extern __shared__ __align__(16) unsigned char fan_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -162,10 +252,10 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
     const int sxs = a.nzp, sys = a.nxp * a.nzp;
     const int xmaxc = (int)a.hix - 1, ymaxc = (int)a.hiy - 1;    // last in-plane cell whose +1 neighbour exists
     const float szf = (float)sz;
-    const int g = lane / LQ, q = lane % LQ;                       // phase-1 role: stream g, z quad q
     const double dx = A.ox + u * A.ux - sx, dy = A.oy + u * A.uy - sy;
     const double dxy2 = dx * dx + dy * dy;
     const double racc = 1.0 / a.acc;
+    const double dz0 = A.oz + (double)V0 * A.vz - sz;             // P_z - S_z of the tile's row 0; +vz per row
     unsigned my_ns = 0;
     float r2 = 0.f, mymax = -INFINITY;
 
@@ -174,7 +264,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
         int last = -2;
         for (int r0 = 0; r0 < nRows; r0 += 32) {
             const bool in = r0 + lane < nRows;
-            const double dz = A.oz + (double)(V0 + r0 + lane) * A.vz - sz;
+            const double dz = dz0 + (double)(r0 + lane) * A.vz;
             const int n = in ? (int)ceil(sqrt(dxy2 + dz * dz) * racc) : -1;
             int prev = __shfl_up_sync(0xffffffffu, n, 1);
             if (lane == 0) prev = last;
@@ -189,7 +279,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
     while (cur < nRows) {
         // ---- the run of rows [cur, e) that share n (uniform over the warp)
         const int e = fan_next_start(sm.starts, cur, nRows);
-        const double dzc = A.oz + (double)(V0 + cur) * A.vz - sz;
+        const double dzc = dz0 + (double)cur * A.vz;
         const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
         const double rn = 1.0 / (double)nrun;
         const double ddx = dx * rn, ddy = dy * rn;
@@ -197,220 +287,136 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
         bool hit = true;
         fan_slab(sx, ddx, 0.0, (double)a.hix, t0, t1, hit);
         fan_slab(sy, ddy, 0.0, (double)a.hiy, t0, t1, hit);
-        const int len = e - cur;
-        const int npieces = (len + a.fan_piece - 1) / a.fan_piece;
-        const int psz = (len + npieces - 1) / npieces;
-        for (int pa = cur; pa < e; pa += psz) {
-            const int pb = min(e, pa + psz);
-            // ---- this lane's rows of the piece: pa + lane + 32 m
-            double ddz[RPL];
-            int i0[RPL], i1[RPL];
-            float sum[RPL], fdz[RPL], inv[RPL];
-            int I0 = INT_MAX, I1 = -1;
+        // ---- rows of the run: clear their sums, count their samples, find the run's step range
+        int I0 = INT_MAX, I1 = -1;
+        for (int r = cur + lane; r < e; r += 32) {
+            sm.rsum[r] = 0.f;
+            double tz0 = t0, tz1 = t1;
+            bool hz = hit;
+            fan_slab(sz, (dz0 + (double)r * A.vz) * rn, zlo, zhi, tz0, tz1, hz);
+            if (hz && tz0 <= tz1) {
+                const int i0 = (int)ceil(tz0), i1 = (int)floor(tz1);
+                if (i0 <= i1) { I0 = min(I0, i0); I1 = max(I1, i1); my_ns += (unsigned)(i1 - i0 + 1); }
+            }
+        }
+        I0 = __reduce_min_sync(0xffffffffu, I0);
+        I1 = __reduce_max_sync(0xffffffffu, I1);
+        if (I0 <= I1) {
+            // z (slices) of row r at step j:  sz + j * (zr0 + r * zvr)
+            const double zr0 = dz0 * rn, zvr = A.vz * rn;
+            const float fI0 = (float)I0, fI1 = (float)I1;
+#pragma unroll 1
+            for (int c0 = I0; c0 <= I1; c0 += CW) {
+                const int nst = min(CW, I1 - c0 + 1);             // steps of this chunk
+                __syncwarp();                                     // the previous chunk is done with w/off
+                // ---- phase 0, once per (run, chunk): in-plane cell and bilinear weights of every step.
+                // The chunk origin is split in double into an integer cell and a fraction; steps add t*d
+                // to the fraction in fp32 (|t| < CW): a position is good to ~2e-6 voxels, nothing accumulates.
+                {
+                    const double ex = sx + (double)c0 * ddx, ey = sy + (double)c0 * ddy;
+                    const double exi = floor(ex), eyi = floor(ey);
+                    const float exf = (float)(ex - exi), eyf = (float)(ey - eyi);
+                    const int exc = (int)exi, eyc = (int)eyi;
+                    const float fddx = (float)ddx, fddy = (float)ddy;
 #pragma unroll
-            for (int m = 0; m < RPL; ++m) {
-                const int r = pa + lane + 32 * m;
-                ddz[m] = (A.oz + (double)(V0 + r) * A.vz - sz) * rn;
-                i0[m] = 0; i1[m] = -1; sum[m] = 0.f;
-                fdz[m] = (float)ddz[m];
-                inv[m] = 1.f / fabsf(fdz[m]);
-                if (r < pb) {
-                    double tz0 = t0, tz1 = t1;
-                    bool hz = hit;
-                    fan_slab(sz, ddz[m], zlo, zhi, tz0, tz1, hz);
-                    if (hz && tz0 <= tz1) { i0[m] = (int)ceil(tz0); i1[m] = (int)floor(tz1); }
-                    if (i0[m] <= i1[m]) {
-                        I0 = min(I0, i0[m]); I1 = max(I1, i1[m]);
-                        my_ns += (unsigned)(i1[m] - i0[m] + 1);
+                    for (int t = lane; t < CW; t += 32) {
+                        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                        unsigned off = 0;
+                        if (t < nst) {
+                            const float px = fmaf((float)t, fddx, exf), py = fmaf((float)t, fddy, eyf);
+                            const float flx = floorf(px), fly = floorf(py);
+                            const int cx = min(max(exc + (int)flx, 0), xmaxc);
+                            const int cy = min(max(eyc + (int)fly, 0), ymaxc);
+                            // fraction against the CLAMPED cell: a sample the double clip admitted may sit
+                            // an ulp outside in fp32, and must then weigh the rim, not the next column
+                            const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
+                            const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
+                            off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
+                            const float gx = 1.f - fx, gy = 1.f - fy;
+                            w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
+                        }
+                        sm.w[t + (t >> LOGB)] = w;
+                        sm.off[t + (t >> LOGB)] = off;
                     }
                 }
-            }
-            I0 = __reduce_min_sync(0xffffffffu, I0);
-            I1 = __reduce_max_sync(0xffffffffu, I1);
-            if (I0 <= I1) {
-                // z slopes per step of the piece's first and last row: the corners of every z window
-                const float fdzA = (float)((A.oz + (double)(V0 + pa) * A.vz - sz) * rn);
-                const float fdzB = (float)((A.oz + (double)(V0 + pb - 1) * A.vz - sz) * rn);
-                // phase 0 + z window of the chunk starting at step c0; also asks L1 for the chunk's
-                // corner columns, so that phase 1 (which runs after the previous chunk's phase 2) finds them
-                auto prep = [&](const int c0, int &kA, int &nq, int &nst) {
-                    nst = min(CW, I1 - c0 + 1);                   // steps of this chunk
-                    // ---- phase 0: in-plane cell and bilinear weights of every step.  The chunk origin is
-                    // split in double into an integer cell and a fraction; steps add t*d to the fraction in
-                    // fp32 (|t| < CW), so a position is good to ~2e-6 voxels and nothing accumulates.
-                    {
-                        const double ex = sx + (double)c0 * ddx, ey = sy + (double)c0 * ddy;
-                        const double exi = floor(ex), eyi = floor(ey);
-                        const float exf = (float)(ex - exi), eyf = (float)(ey - eyi);
-                        const int exc = (int)exi, eyc = (int)eyi;
-                        const float fddx = (float)ddx, fddy = (float)ddy;
-#pragma unroll
-                        for (int t = lane; t < CW; t += 32) {
-                            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                            unsigned off = 0;
-                            if (t < nst) {
-                                const float px = fmaf((float)t, fddx, exf), py = fmaf((float)t, fddy, eyf);
-                                const float flx = floorf(px), fly = floorf(py);
-                                const int cx = min(max(exc + (int)flx, 0), xmaxc);
-                                const int cy = min(max(eyc + (int)fly, 0), ymaxc);
-                                // fraction against the CLAMPED cell: a sample the double clip admitted may sit
-                                // an ulp outside in fp32, and must then weigh the rim, not the next column
-                                const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
-                                const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
-                                off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
-                                const float gx = 1.f - fx, gy = 1.f - fy;
-                                w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
-                            }
-                            sm.w[t + (t >> LOGB)] = w;
-                            sm.off[t + (t >> LOGB)] = off;
-                        }
-                    }
-                    // ---- z window of the chunk: all rows of the piece x all its steps (uniform)
-                    {
-                        const float ja = (float)c0, jb = (float)(c0 + nst - 1);
-                        const float z0 = fmaf(ja, fdzA, szf), z1 = fmaf(ja, fdzB, szf);
-                        const float z2 = fmaf(jb, fdzA, szf), z3 = fmaf(jb, fdzB, szf);
-                        const float zmin = fminf(fminf(z0, z1), fminf(z2, z3));
-                        const float zmax = fmaxf(fmaxf(z0, z1), fmaxf(z2, z3));
-                        kA = max(kmin, (int)floorf(zmin - 2e-3f)) & ~3;
-                        const int kB = min(kmax, (int)floorf(zmax + 2e-3f) + 1);
-                        nq = (kB - kA + 4) >> 2;                  // quads in the window; <= LQ by the piece
-                        if (nq > LQ && lane == 0 && a.fault)      // size pax_fan_configure chose
-                            atomicExch(a.fault, 1);
-                    }
-                    if (a.fan_prefetch && nq > 0) {
-                        const char *vb = reinterpret_cast<const char *>(a.vol0 + kA);
-                        const int span = 16 * nq - 4;             // last byte offset of the window, floats*4
-#pragma unroll
-                        for (int t = lane; t < CW; t += 32) {
-                            if (t < nst) {
-                                const char *p = vb + sm.off[t + (t >> LOGB)];
-                                fan_prefetch_l1(p); fan_prefetch_l1(p + span);
-                                fan_prefetch_l1(p + sxs * 4); fan_prefetch_l1(p + sxs * 4 + span);
-                                fan_prefetch_l1(p + sys * 4); fan_prefetch_l1(p + sys * 4 + span);
-                                fan_prefetch_l1(p + (sys + sxs) * 4); fan_prefetch_l1(p + (sys + sxs) * 4 + span);
-                            }
-                        }
-                    }
-                };
-                int kA, nq, nst;
-                prep(I0, kA, nq, nst);
+                // z of row r at the first / last step of the chunk: Aa + Ba r, Ab + Bb r  (Ba, Bb >= 0)
+                const double ja = (double)c0, jb = (double)(c0 + nst - 1);
+                const float Aa = (float)(sz + ja * zr0), Ba = (float)(ja * zvr);
+                const float Ab = (float)(sz + jb * zr0), Bb = (float)(jb * zvr);
+                // (approximate reciprocals: the row bounds below are re-checked against the window)
+                const float rBa = Ba > 0.f ? __frcp_rn(Ba) : 0.f, rBb = Bb > 0.f ? __frcp_rn(Bb) : 0.f;
+                // rows that can touch a slice during this chunk
+                int ga = cur, ge = e;
+                {
+                    const float lo_a = Ba > 0.f ? (kminf - 1.f - Aa) * rBa : (Aa >= kminf - 1.f ? -1e9f : 1e9f);
+                    const float lo_b = Bb > 0.f ? (kminf - 1.f - Ab) * rBb : (Ab >= kminf - 1.f ? -1e9f : 1e9f);
+                    const float hi_a = Ba > 0.f ? (kmaxf + 1.f - Aa) * rBa : (Aa <= kmaxf + 1.f ? 1e9f : -1e9f);
+                    const float hi_b = Bb > 0.f ? (kmaxf + 1.f - Ab) * rBb : (Ab <= kmaxf + 1.f ? 1e9f : -1e9f);
+                    ga = max(ga, (int)fmaxf(fminf(ceilf(fminf(lo_a, lo_b)), 1e6f), -1e6f));
+                    ge = min(ge, (int)fmaxf(fminf(floorf(fmaxf(hi_a, hi_b)), 1e6f), -1e6f) + 1);
+                }
+                __syncwarp();
+                // ---- groups of rows whose z window over this chunk fits the W slices of a stream
 #pragma unroll 1
-                for (int c0 = I0; c0 <= I1; c0 += CW) {
-                    __syncwarp();
-                    // ---- phase 1: stream-local running sums, four slices per lane
-                    {
-                        const bool on = q < nq;
-                        const float *__restrict__ base = a.vol0 + kA + 4 * q;
-                        float2 pq0 = make_float2(0.f, 0.f), pq1 = pq0, pq2 = pq0, pq3 = pq0;   // running (P,Q) x 4 slices
-                        float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
-                        const int row0 = g * (B + 1);             // table row of the stream's first step
-                        const float4 *wp = sm.w + row0;
-                        const unsigned *op = sm.off + row0;
-                        float4 *Tw = reinterpret_cast<float4 *>(sm.T + row0 * TS + 4 * q);
-                        float jf = (float)(g * B - CW / 2);
-                        if (g * B < nst) {
-                            // The corner columns of step s+1 are requested (predicated, no branch) right after
-                            // step s has consumed the registers, so the running-sum updates, the table stores
-                            // and the next step's address arithmetic cover part of the L2 latency.
-                            // byte offsets are unsigned 32-bit (pax_ax_fan_launch checks the volume is < 4 GB):
-                            // one 64-bit add per step, the other corners are uniform strides away
-                            const char *bb = reinterpret_cast<const char *>(base);
-                            const size_t dx4 = (size_t)sxs * 4, dy4 = (size_t)sys * 4;
-                            unsigned off = op[0];
-                            {
-                                const char *p00 = bb + off, *p10 = p00 + dy4;
-                                fan_ld4_if(c00, p00, on); fan_ld4_if(c01, p00 + dx4, on);
-                                fan_ld4_if(c10, p10, on); fan_ld4_if(c11, p10 + dx4, on);
-                            }
-                            float4 w = wp[0];
-#pragma unroll
-                            for (int s = 0; s < B; ++s) {
-                                unsigned offn = off;
-                                float4 wn = w;
-                                if (s + 1 < B) { offn = op[s + 1]; wn = wp[s + 1]; }
-                                const bool chg = on && offn != off;
-                                const char *p00 = bb + offn, *p10 = p00 + dy4;
-                                const char *p01 = p00 + dx4, *p11 = p10 + dx4;
-                                float2 v0 = fan_mul2(w.x, c00.x, c00.y), v1 = fan_mul2(w.x, c00.z, c00.w);
-                                v0 = fan_fma2(w.y, c01.x, c01.y, v0); v1 = fan_fma2(w.y, c01.z, c01.w, v1);
-                                v0 = fan_fma2(w.z, c10.x, c10.y, v0); v1 = fan_fma2(w.z, c10.z, c10.w, v1);
-                                v0 = fan_fma2(w.w, c11.x, c11.y, v0); v1 = fan_fma2(w.w, c11.z, c11.w, v1);
-                                if (s + 1 < B) {
-                                    fan_ld4_if(c00, p00, chg); fan_ld4_if(c01, p01, chg);
-                                    fan_ld4_if(c10, p10, chg); fan_ld4_if(c11, p11, chg);
-                                }
-                                pq0.x += v0.x; pq1.x += v0.y; pq2.x += v1.x; pq3.x += v1.y;
-                                pq0.y = fmaf(jf, v0.x, pq0.y); pq1.y = fmaf(jf, v0.y, pq1.y);
-                                pq2.y = fmaf(jf, v1.x, pq2.y); pq3.y = fmaf(jf, v1.y, pq3.y);
-                                jf += 1.f;
-                                if (on) {
-                                    Tw[s * (TS / 2)] = make_float4(pq0.x, pq0.y, pq1.x, pq1.y);
-                                    Tw[s * (TS / 2) + 1] = make_float4(pq2.x, pq2.y, pq3.x, pq3.y);
-                                }
-                                off = offn;
-                                w = wn;
-                            }
-                        }
-                        // carry of a stream = totals of the earlier streams: inclusive scan over g, minus own
-                        float2 t0 = pq0, t1 = pq1, t2 = pq2, t3 = pq3;
-#pragma unroll
-                        for (int d = LQ; d < 32; d <<= 1) {
-                            const float2 o0 = fan_shfl_up2(t0, d), o1 = fan_shfl_up2(t1, d);
-                            const float2 o2 = fan_shfl_up2(t2, d), o3 = fan_shfl_up2(t3, d);
-                            if (lane >= d) {
-                                t0 = __fadd2_rn(t0, o0); t1 = __fadd2_rn(t1, o1);
-                                t2 = __fadd2_rn(t2, o2); t3 = __fadd2_rn(t3, o3);
-                            }
-                        }
-                        float4 *cw = reinterpret_cast<float4 *>(sm.carry + g * TS + 4 * q);
-                        cw[0] = make_float4(t0.x - pq0.x, t0.y - pq0.y, t1.x - pq1.x, t1.y - pq1.y);
-                        cw[1] = make_float4(t2.x - pq2.x, t2.y - pq2.y, t3.x - pq3.x, t3.y - pq3.y);
-                        if (g == G - 1) {                           // inclusive total of the last stream = chunk total
-                            float4 *tw = reinterpret_cast<float4 *>(sm.total + 4 * q);
-                            tw[0] = make_float4(t0.x, t0.y, t1.x, t1.y);
-                            tw[1] = make_float4(t2.x, t2.y, t3.x, t3.y);
-                        }
+                while (ga < ge) {
+                    const float fga = (float)ga;
+                    const float zmin = fminf(fmaf(Ba, fga, Aa), fmaf(Bb, fga, Ab));
+                    const int kA = max(kmin, (int)floorf(zmin - 2e-3f)) & ~3;
+                    int gb = min(ge, ga + a.fan_piece);
+                    if (kA + W - 1 < kmax) {
+                        // floor(zmax + eps) + 1 <= kA + W - 1  for both ends of the chunk
+                        const float lim = (float)(kA + W - 1) - 4e-3f;
+                        const float ra = Ba > 0.f ? (lim - Aa) * rBa : 1e9f, rb = Bb > 0.f ? (lim - Ab) * rBb : 1e9f;
+                        gb = min(gb, (int)fmaxf(fminf(floorf(fminf(ra, rb) - 1e-2f), 1e6f), -1e6f) + 1);
                     }
-                    __syncwarp();
-                    // ---- the next chunk's phase 0 (w/off are free again) and its L1 prefetch, hidden
-                    // behind this chunk's phase 2
-                    int kA2 = 0, nq2 = 0, nst2 = 0;
-                    if (c0 + CW <= I1) prep(c0 + CW, kA2, nq2, nst2);
-                    // ---- phase 2: the lane's detector rows, one table look-up pair per stretch end
-#pragma unroll
-                    for (int m = 0; m < RPL; ++m) {
-                        const int lo = max(i0[m], c0) - c0, hi = min(i1[m], c0 + CW - 1) - c0;   // chunk-local
-                        if (lo <= hi) {
-                            const float dzf = fdz[m];
-                            const float zc0 = (float)(sz + (double)c0 * ddz[m]);
-                            const float jc = (float)(CW / 2);
-                            float zl = fmaf((float)lo, dzf, zc0);
-                            const float zh = fmaf((float)hi, dzf, zc0);
-                            // fp32 z may round onto the clip bounds the double range excluded: keep the
-                            // slice pair inside [kmin, kmax] (tt then extrapolates by an ulp)
-                            float kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
-                            float acc;
-                            if (lo == 0 && hi == nst - 1 && floorf(zh) == kf) {
-                                // the row spans the whole chunk inside one slice pair: the chunk totals
-                                const int kk = min(max((int)kf - kA, 0), W - 2);
-                                const float2 b0 = sm.total[kk], b1 = sm.total[kk + 1];
-                                const float alpha = fmaf(jc, dzf, zl - kf);            // lo == 0
-                                acc = fmaf(dzf, b1.y - b0.y, fmaf(alpha, b1.x - b0.x, b0.x));
-                            } else {
-                                acc = 0.f;
-                                const float rinv = inv[m];
+                    if (gb <= ga) {                               // a single row does not fit: see pax_fan_configure
+                        if (lane == 0 && a.fault) atomicExch(a.fault, 1);
+                        gb = ga + 1;
+                    }
+                    const float fgl = (float)(gb - 1);
+                    const float zmax = fmaxf(fmaf(Ba, fgl, Aa), fmaf(Bb, fgl, Ab));
+                    const int kB = min(kmax, (int)floorf(zmax + 2e-3f) + 1);
+                    const int nq = (kB - kA + 4) >> 2;            // quads in the window
+                    if (nq > LQ && lane == 0 && a.fault) atomicExch(a.fault, 3);
+                    if (nq > 0) {
+                        fan_phase1<LQ, SB>(sm, a.vol0, sxs, sys, kA, nq, nst, lane);
+                        __syncwarp();
+                        // ---- phase 2: one detector row per lane and pass
+                        for (int r = ga + lane; r < gb; r += 32) {
+                            const double ddz = zr0 + (double)r * zvr;
+                            const float dzf = (float)ddz;
+                            // the row's own step range, re-derived in fp32 (the double version counted the
+                            // samples; a boundary sample has zero weight, so an ulp either way is harmless)
+                            float flo = fI0, fhi = fI1;
+                            const float rz = __frcp_rn(dzf);              // inf when dzf == 0: not used then
+                            if (dzf != 0.f) {
+                                const float ta = (kminf - szf) * rz, tb = (kmaxf - szf) * rz;
+                                flo = fmaxf(flo, ceilf(fminf(ta, tb)));
+                                fhi = fminf(fhi, floorf(fmaxf(ta, tb)));
+                            } else if (!(szf >= kminf && szf < kmaxf)) {
+                                fhi = -1.f;
+                            }
+                            const int lo = max((int)flo, c0) - c0, hi = min((int)fhi, c0 + nst - 1) - c0;
+                            if (lo <= hi) {
+                                const float rinv = fabsf(rz);
+                                const float zc0 = (float)(sz + (double)c0 * ddz);
+                                const float jc = (float)(CW / 2);
+                                float zl = fmaf((float)lo, dzf, zc0);
+                                // fp32 z may round onto the clip bounds: keep the slice pair inside
+                                // [kmin, kmax] (tt then extrapolates by an ulp)
+                                float kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
+                                const bool up = dzf > 0.f;
+                                float acc = 0.f;
                                 int j = lo;
-                                while (j <= hi) {
+                                do {
                                     const float tt = zl - kf;
-                                    // steps that stay in slice pair (k, k+1)
-                                    int ms;
-                                    if (dzf > 0.f) ms = (int)fminf(ceilf((1.f - tt) * rinv), 1.0e4f) - 1;
-                                    else if (dzf < 0.f) ms = (int)fminf(floorf(tt * rinv), 1.0e4f);
-                                    else ms = CW;
+                                    // steps that stay in slice pair (k, k+1): tt + m dz stays inside [0,1).  An
+                                    // exact hit of the boundary may go either way (the interpolant is continuous);
+                                    // dz == 0 gives inf or NaN here, which fminf turns into "the rest of the chunk".
+                                    const int ms = (int)fminf(floorf((up ? 1.f - tt : tt) * rinv), 1.0e4f);
                                     const int je = min(hi, j + max(ms, 0));
                                     int kk = (int)kf - kA;
-                                    if (kk < 0 || kk > 4 * nq - 2) {           // cannot happen: see pax_fan_configure
+                                    if (kk < 0 || kk > 4 * nq - 2) {           // cannot happen: the group was cut to fit
                                         if (a.fault) atomicExch(a.fault, 2);
                                         kk = min(max(kk, 0), W - 2);
                                     }
@@ -419,43 +425,41 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
                                     fan_lookup<LQ, SB>(sm.T, sm.carry, je, kk, b0, b1);
                                     const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
                                     const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
-                                    const float alpha = fmaf(jc - (float)j, dzf, tt);  // t at index CW/2
+                                    const float alpha = fmaf(jc - (float)j, dzf, tt);      // t at index CW/2
                                     acc += fmaf(dzf, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
                                     j = je + 1;
                                     zl = fmaf((float)j, dzf, zc0);
                                     kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
-                                }
+                                } while (j <= hi);
+                                sm.rsum[r] += acc;
                             }
-                            sum[m] += acc;
                         }
+                        __syncwarp();                             // the table is free for the next group
                     }
-                    kA = kA2; nq = nq2; nst = nst2;
+                    ga = gb;
                 }
             }
-            // ---- epilogue of the piece.  The eight warps of the CTA own eight adjacent columns and
-            // fill one 32-byte sector of every row between them; L2 merges the partial writes.
-#pragma unroll
-            for (int m = 0; m < RPL; ++m) {
-                const int r = pa + lane + 32 * m;
-                if (r < pb) {
-                    const int v = V0 + r;
-                    const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
-                    const double mx = ddx * a.dX, my = ddy * a.dY, mz = ddz[m] * a.dZ;
-                    const float p0 = sum[m] * (float)sqrt(mx * mx + my * my + mz * mz);
-                    if (MODE == PAX_AX_PLAIN) {
-                        float val = a.a0 * p0;
-                        if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
-                        if (a.accumulate) val += a.out[o];
-                        a.out[o] = val;
-                        mymax = fmaxf(mymax, val);
-                    } else {
-                        const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
-                        const float w = L > a.wthr ? 1.f / L : 0.f;
-                        const float r_ = __ldg(a.b + o) - p0;
-                        r2 = fmaf(r_, r_, r2);
-                        a.out[o] = w * r_;
-                    }
-                }
+        }
+        __syncwarp();
+        // ---- epilogue of the run.  The warps of the CTA own adjacent columns and fill one 32-byte sector
+        // of every row between them; L2 merges the partial writes.
+        for (int r = cur + lane; r < e; r += 32) {
+            const int v = V0 + r;
+            const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
+            const double mx = ddx * a.dX, my = ddy * a.dY, mz = (dz0 + (double)r * A.vz) * rn * a.dZ;
+            const float p0 = sm.rsum[r] * (float)sqrt(mx * mx + my * my + mz * mz);
+            if (MODE == PAX_AX_PLAIN) {
+                float val = a.a0 * p0;
+                if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
+                if (a.accumulate) val += a.out[o];
+                a.out[o] = val;
+                mymax = fmaxf(mymax, val);
+            } else {
+                const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
+                const float w = L > a.wthr ? 1.f / L : 0.f;
+                const float r_ = __ldg(a.b + o) - p0;
+                r2 = fmaf(r_, r_, r2);
+                a.out[o] = w * r_;
             }
         }
         cur = e;
@@ -518,11 +522,14 @@ int pax_fan_configure(PaxPlan *p)
     int lq = (p8 > 3 * p4) ? 8 : 4;                             // (measured at C2: 12.1 ms vs 10.0 ms)
     if (force && (atoi(force) == 4 || atoi(force) == 8)) lq = atoi(force);
     p->fan_lq = lq;
-    p->fan_piece = lq == 8 ? p8 : p4;
+    // worst-case number of rows whose z window fits (AUTO's criterion, pax_plan_fan_info); the kernel
+    // itself cuts the groups per chunk from the actual z range, up to FAN_GROUP rows
+    p->fan_fit = lq == 8 ? p8 : p4;
+    p->fan_piece = p->fan_fit >= 1 ? FAN_GROUP : 0;
     p->fan_warps = lq == 8 ? FAN_NW8 : FAN_NW;
-    // rows one warp walks: whole columns when short, else equal tiles of <= 512 rows
-    const int tiles = (g.nDetecV + 511) / 512;
-    p->fan_rows = std::min(FAN_MAXTILE, (g.nDetecV + tiles - 1) / tiles);
+    // rows one warp walks: whole columns when short, else equal tiles of <= FAN_MAXTILE rows
+    const int tiles = (g.nDetecV + FAN_MAXTILE - 1) / FAN_MAXTILE;
+    p->fan_rows = (g.nDetecV + tiles - 1) / tiles;
     // mean run length of equal n over three columns of the first angle
     {
         const AngleDev &A = p->h_angles[0];

@@ -38,7 +38,8 @@ struct PaxPlan {
     std::vector<AngleDev> h_angles;
     int projector;              // PAX_PROJECTOR_* requested (AUTO resolves per call)
     int fan_rows;               // ax_fan.cu: detector rows one warp walks
-    int fan_piece;              // most rows whose z window fits the lanes of a stream (0: FAN does not fit)
+    int fan_piece;              // most rows summed from one set of tables (0: FAN does not fit the geometry)
+    int fan_fit;                // worst-case rows whose z window fits the lanes of a stream
     int fan_lq;                 // lanes per step (4: 16-slice windows, 8: 32-slice windows)
     int fan_warps;              // warps per CTA
     double fan_run;             // mean length (rows) of the equal-n runs of a detector column

@@ -121,13 +121,13 @@ extern "C" int pax_plan_projector(const PaxPlan *p)
     if (p->projector != PAX_PROJECTOR_AUTO) return p->projector;
     // FAN pays when many rows share one lattice (long runs of equal n) and a piece of them fits the
     // lanes; measured at C2 (mean run 154 rows, pieces of 64): 9.4 ms vs 18.6 ms per 20-angle subset
-    return (p->fan_piece >= 32 && p->fan_run >= 48.0) ? PAX_PROJECTOR_FAN : PAX_PROJECTOR_RAY;
+    return (p->fan_fit >= 32 && p->fan_run >= 48.0) ? PAX_PROJECTOR_FAN : PAX_PROJECTOR_RAY;
 }
 
 extern "C" int pax_plan_fan_info(const PaxPlan *p, int *rows_per_tile, int *warps, double *mean_run)
 {
     PAX_REQUIRE(p, "pax_plan_fan_info: NULL plan");
-    if (rows_per_tile) *rows_per_tile = p->fan_piece;
+    if (rows_per_tile) *rows_per_tile = p->fan_fit;
     if (warps) *warps = p->fan_warps;
     if (mean_run) *mean_run = p->fan_run;
     return PAX_OK;

@@ -24,22 +24,22 @@ def main(rep, top=40, only=None):
             d = dict(zip(hdr[4:], r[4:]))
             key = (fname, int(r[0]))
             e = agg.setdefault(key, {"src": r[1], "inst": 0, "smp": 0, "long_sb": 0, "barrier": 0, "short_sb": 0,
-                                     "wait": 0, "mio": 0})
+                                     "wait": 0, "mio": 0, "branch": 0})
             e["inst"] += int(d.get("Instructions Executed", 0) or 0)
             e["smp"] += int(d.get("# Samples", 0) or 0)
             for k, c in (("long_sb", "stall_long_sb"), ("barrier", "stall_barrier"), ("short_sb", "stall_short_sb"),
-                         ("wait", "stall_wait"), ("mio", "stall_mio")):
+                         ("wait", "stall_wait"), ("mio", "stall_mio"), ("branch", "stall_branch_resolving")):
                 e[k] += int(d.get(c, 0) or 0)
     ti = sum(e["inst"] for e in agg.values()) or 1
     ts = sum(e["smp"] for e in agg.values()) or 1
     print(f"total warp instructions {ti:.3e}, samples {ts}")
     items = [(k, e) for k, e in agg.items() if only is None or only in k[0]]
     items.sort(key=lambda ke: -ke[1]["smp"])
-    print(" inst%  smp%  long barr shrt wait  mio  file:line  source")
+    print(" inst%  smp%  long barr shrt wait  mio  brch  file:line  source")
     for (f, ln), e in items[:top]:
         print(f"{100 * e['inst'] / ti:5.1f} {100 * e['smp'] / ts:5.1f} "
               f"{100 * e['long_sb'] / ts:5.1f} {100 * e['barrier'] / ts:4.1f} {100 * e['short_sb'] / ts:4.1f} "
-              f"{100 * e['wait'] / ts:4.1f} {100 * e['mio'] / ts:4.1f}  {f}:{ln}  {e['src'].strip()[:90]}")
+              f"{100 * e['wait'] / ts:4.1f} {100 * e['mio'] / ts:4.1f} {100 * e['branch'] / ts:4.1f}  {f}:{ln}  {e['src'].strip()[:90]}")
 
 
 if __name__ == "__main__":
