@@ -229,6 +229,73 @@ __device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float 
         }
 }
 
+// ---- phase 2 state of one detector row within a chunk
+struct FanRow {
+    float dzf, rinv, zc0, zl, kf, acc;
+    int j, hi;
+    bool up, bad;
+
+    // the row's own step range is re-derived in fp32 (the double version counted the samples; a boundary
+    // sample has zero weight, so an ulp either way is harmless)
+    __device__ __forceinline__ void init(int r, bool exists, double zr0, double zvr, double sz, float szf,
+                                         float kminf, float kmaxf, float fI0, float fI1, int c0, int nst)
+    {
+        const double ddz = zr0 + (double)r * zvr;
+        dzf = (float)ddz;
+        float flo = fI0, fhi = exists ? fI1 : -1.f;
+        const float rz = __frcp_rn(dzf);                      // inf when dzf == 0: not used then
+        if (dzf != 0.f) {
+            const float ta = (kminf - szf) * rz, tb = (kmaxf - szf) * rz;
+            flo = fmaxf(flo, ceilf(fminf(ta, tb)));
+            fhi = fminf(fhi, floorf(fmaxf(ta, tb)));
+        } else if (!(szf >= kminf && szf < kmaxf)) {
+            fhi = -1.f;
+        }
+        j = max((int)flo, c0) - c0;
+        hi = min((int)fhi, c0 + nst - 1) - c0;
+        if (j > hi) j = max(hi, -1) + 1;                      // nothing to do here: keep the look-up indices in range
+        rinv = fabsf(rz);
+        up = dzf > 0.f;
+        zc0 = (float)(sz + (double)c0 * ddz);
+        zl = fmaf((float)j, dzf, zc0);
+        // fp32 z may round onto the clip bounds: keep the slice pair inside [kmin, kmax] (tt then
+        // extrapolates by an ulp)
+        kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
+        acc = 0.f;
+        bad = false;
+    }
+
+    // one stretch (the steps from j on that stay in one slice pair), branch-free; a no-op once j > hi
+    template <int LQ, int SB>
+    __device__ __forceinline__ void stretch(const float2 *T, const float2 *carry, int kA, int nq, float kminf,
+                                            float kmaxf)
+    {
+        constexpr int W = FanCfg<LQ, SB>::W, CW = FanCfg<LQ, SB>::CW;
+        const bool live = j <= hi;
+        const float tt = zl - kf;
+        // steps that stay in slice pair (k, k+1): tt + m dz stays inside [0,1).  An exact hit of the boundary
+        // may go either way (the interpolant is continuous); dz == 0 gives inf or NaN here, which fminf turns
+        // into "the rest of the chunk".
+        const int ms = (int)fminf(floorf((up ? 1.f - tt : tt) * rinv), 1.0e4f);
+        const int je = max(min(hi, j + max(ms, 0)), 0);
+        const int kr = (int)kf - kA;
+        const int kk = min(max(kr, 0), W - 2);
+        bad |= live && (kr < 0 || kr > 4 * nq - 2);
+        float2 a0, a1, b0, b1;
+        fan_lookup<LQ, SB>(T, carry, max(j - 1, 0), kk, a0, a1);
+        fan_lookup<LQ, SB>(T, carry, je, kk, b0, b1);
+        if (j <= 0) { a0 = make_float2(0.f, 0.f); a1 = a0; }
+        const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
+        const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
+        const float alpha = fmaf((float)(CW / 2 - j), dzf, tt);                // t at index CW/2
+        const float val = fmaf(dzf, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
+        acc += live ? val : 0.f;
+        j = live ? je + 1 : j;
+        zl = fmaf((float)j, dzf, zc0);
+        kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
+    }
+};
+
 template <int LQ, int SB, int RPL, int NWARPS, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
 {
@@ -258,6 +325,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
     const double dz0 = A.oz + (double)V0 * A.vz - sz;             // P_z - S_z of the tile's row 0; +vz per row
     unsigned my_ns = 0;
     float r2 = 0.f, mymax = -INFINITY;
+    bool bad = false;
 
     // ---- runs of rows with equal n = ceil(|P-S| / accuracy)  (TIGRE's lattice)
     {
@@ -381,59 +449,21 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
                     if (nq > 0) {
                         fan_phase1<LQ, SB>(sm, a.vol0, sxs, sys, kA, nq, nst, lane);
                         __syncwarp();
-                        // ---- phase 2: one detector row per lane and pass
-                        for (int r = ga + lane; r < gb; r += 32) {
-                            const double ddz = zr0 + (double)r * zvr;
-                            const float dzf = (float)ddz;
-                            // the row's own step range, re-derived in fp32 (the double version counted the
-                            // samples; a boundary sample has zero weight, so an ulp either way is harmless)
-                            float flo = fI0, fhi = fI1;
-                            const float rz = __frcp_rn(dzf);              // inf when dzf == 0: not used then
-                            if (dzf != 0.f) {
-                                const float ta = (kminf - szf) * rz, tb = (kmaxf - szf) * rz;
-                                flo = fmaxf(flo, ceilf(fminf(ta, tb)));
-                                fhi = fminf(fhi, floorf(fmaxf(ta, tb)));
-                            } else if (!(szf >= kminf && szf < kmaxf)) {
-                                fhi = -1.f;
+                        // ---- phase 2: two detector rows per lane and pass, advanced side by side so that their
+                        // (serial) address and look-up chains overlap
+                        for (int r = ga + lane; r < gb; r += 64) {
+                            FanRow ra, rb;
+                            ra.init(r, true, zr0, zvr, sz, szf, kminf, kmaxf, fI0, fI1, c0, nst);
+                            rb.init(r + 32, r + 32 < gb, zr0, zvr, sz, szf, kminf, kmaxf, fI0, fI1, c0, nst);
+                            while (ra.j <= ra.hi || rb.j <= rb.hi) {
+                                ra.template stretch<LQ, SB>(sm.T, sm.carry, kA, nq, kminf, kmaxf);
+                                rb.template stretch<LQ, SB>(sm.T, sm.carry, kA, nq, kminf, kmaxf);
                             }
-                            const int lo = max((int)flo, c0) - c0, hi = min((int)fhi, c0 + nst - 1) - c0;
-                            if (lo <= hi) {
-                                const float rinv = fabsf(rz);
-                                const float zc0 = (float)(sz + (double)c0 * ddz);
-                                const float jc = (float)(CW / 2);
-                                float zl = fmaf((float)lo, dzf, zc0);
-                                // fp32 z may round onto the clip bounds: keep the slice pair inside
-                                // [kmin, kmax] (tt then extrapolates by an ulp)
-                                float kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
-                                const bool up = dzf > 0.f;
-                                float acc = 0.f;
-                                int j = lo;
-                                do {
-                                    const float tt = zl - kf;
-                                    // steps that stay in slice pair (k, k+1): tt + m dz stays inside [0,1).  An
-                                    // exact hit of the boundary may go either way (the interpolant is continuous);
-                                    // dz == 0 gives inf or NaN here, which fminf turns into "the rest of the chunk".
-                                    const int ms = (int)fminf(floorf((up ? 1.f - tt : tt) * rinv), 1.0e4f);
-                                    const int je = min(hi, j + max(ms, 0));
-                                    int kk = (int)kf - kA;
-                                    if (kk < 0 || kk > 4 * nq - 2) {           // cannot happen: the group was cut to fit
-                                        if (a.fault) atomicExch(a.fault, 2);
-                                        kk = min(max(kk, 0), W - 2);
-                                    }
-                                    float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0, b1;
-                                    if (j > 0) fan_lookup<LQ, SB>(sm.T, sm.carry, j - 1, kk, a0, a1);
-                                    fan_lookup<LQ, SB>(sm.T, sm.carry, je, kk, b0, b1);
-                                    const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
-                                    const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
-                                    const float alpha = fmaf(jc - (float)j, dzf, tt);      // t at index CW/2
-                                    acc += fmaf(dzf, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
-                                    j = je + 1;
-                                    zl = fmaf((float)j, dzf, zc0);
-                                    kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
-                                } while (j <= hi);
-                                sm.rsum[r] += acc;
-                            }
+                            bad |= ra.bad | rb.bad;
+                            sm.rsum[r] += ra.acc;
+                            if (r + 32 < gb) sm.rsum[r + 32] += rb.acc;
                         }
+                        if (bad && a.fault) atomicExch(a.fault, 2);        // cannot happen: the group was cut to fit
                         __syncwarp();                             // the table is free for the next group
                     }
                     ga = gb;
