@@ -191,8 +191,9 @@ def test_choose_shard_auto():
     from physics_arx_b200.dist import choose_shard
     blocks = order_subsets(656, 20)                      # 32 x 20 + 16
     assert choose_shard(blocks, 2) == "angles" and choose_shard(blocks, 4) == "angles"
-    assert choose_shard(blocks, 8) == "rows"
-    assert choose_shard(blocks, 8, "angles") == "angles"
+    assert choose_shard(blocks, 8) == "angles"           # 16- and 20-angle subsets keep 8 ranks busy
+    assert choose_shard(order_subsets(40, 6), 8) == "rows"   # a 4-angle tail would idle half the ranks
+    assert choose_shard(blocks, 8, "rows") == "rows"
     with pytest.raises(ValueError):
         choose_shard(blocks, 2, "columns")
 
