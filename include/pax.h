@@ -173,6 +173,27 @@ int pax_max_decode(uint32_t *word_dev, void *stream);
 int pax_ctnoise(float *proj, size_t n, uint64_t index0, size_t inner, uint64_t outer_stride, double I0,
                 double mean, double std, const float *max_dev, uint64_t seed, void *stream);
 
+/* ---- Artifact-Induction image operations (the reference's ITK command-line tools,
+ * Physics-based-Augmentation/Artifact-Induction/Cpp-Codes, driven by CBCT_pCT_Artifact_adding.sh:45-145).
+ * Arrays are (Z,Y,X) C-order float32 device pointers, X fastest, like the NRRD files the tools exchange. */
+
+/* itk::ResampleImageFilter with LinearInterpolateImageFunction, identity transform, default pixel value:
+ * ResampleImages.cxx:87-102 (cast_short = 1: short pixels, the result is truncated like ITK's static_cast),
+ * ResampleImagesFloat.cxx, AddImages.cxx:40-53, RescaleImage.cxx:44-92 (iso-z branch).
+ * index_map: 12 host doubles, continuous SOURCE index (x,y,z) of DESTINATION index (i,j,k):
+ * cx = m0 i + m1 j + m2 k + m3, cy = m4.., cz = m8..  (from both images' origin/spacing/direction). */
+int pax_resample_linear(const float *src, int snz, int sny, int snx, const double *index_map, float *dst,
+                        int dnz, int dny, int dnx, float default_value, int cast_short, void *stream);
+/* out2_dev[0] = min, out2_dev[1] = max over n floats (device result) */
+int pax_minmax(const float *x, size_t n, float *out2_dev, void *stream);
+/* itk::RescaleIntensityImageFilter to [out_min, out_max], in place; RescaleImage.cxx:99-104 */
+int pax_rescale_intensity(float *x, size_t n, const float *minmax_dev, double out_min, double out_max,
+                          void *stream);
+/* itk::AdaptiveHistogramEqualizationImageFilter(radius, alpha, beta): AdaptiveHistogramMatch.cxx:30-42.
+ * minmax_dev = pax_minmax of src; radius <= 5 (the reference uses 5); dst != src. */
+int pax_plahe(const float *src, int nz, int ny, int nx, int radius, float alpha, float beta,
+              const float *minmax_dev, float *dst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

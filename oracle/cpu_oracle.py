@@ -51,8 +51,15 @@ def _load():
                                        ctypes.c_uint64, _dp]
         lib.oracle_sart_update.argtypes = [_dp, _dp, _dp, ctypes.c_long, ctypes.c_long,
                                            ctypes.c_double, ctypes.c_int]
+        lib.oracle_resample_linear.argtypes = [_dp, ctypes.c_long, ctypes.c_long, ctypes.c_long, _dp, _dp,
+                                               ctypes.c_long, ctypes.c_long, ctypes.c_long,
+                                               ctypes.c_double, ctypes.c_int]
+        lib.oracle_rescale_intensity.argtypes = [_dp, ctypes.c_long, ctypes.c_double, ctypes.c_double, _dp]
+        lib.oracle_plahe.argtypes = [_dp, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long,
+                                     ctypes.c_double, ctypes.c_double, _dp]
         for f in (lib.oracle_ax_interp, lib.oracle_atb_fdk, lib.oracle_raylen_w,
-                  lib.oracle_philox, lib.oracle_ctnoise, lib.oracle_sart_update):
+                  lib.oracle_philox, lib.oracle_ctnoise, lib.oracle_sart_update,
+                  lib.oracle_resample_linear, lib.oracle_rescale_intensity, lib.oracle_plahe):
             f.restype = None
         _lib = lib
     return _lib
@@ -211,3 +218,40 @@ def ossart(proj, geo, angles, niter, blocksize=20, lmbda=1.0, lmbda_red=0.99, no
         l2.append(np.sqrt(err))
         lam *= lmbda_red
     return (x, np.array(l2)) if return_l2 else x
+
+
+# ------------------------------------------------------------------ Artifact-Induction tools
+def index_map(dst_origin, dst_spacing, dst_direction, src_origin, src_spacing, src_direction):
+    """12 doubles: continuous SOURCE index (x,y,z) of DESTINATION index (i,j,k), identity transform
+    (what itk::ResampleImageFilter evaluates; origins/spacings in (x,y,z) order, directions 3x3)."""
+    dd = np.asarray(dst_direction, dtype=np.float64).reshape(3, 3)
+    sd = np.asarray(src_direction, dtype=np.float64).reshape(3, 3)
+    a = np.linalg.inv(sd @ np.diag(np.asarray(src_spacing, dtype=np.float64)))
+    lin = a @ dd @ np.diag(np.asarray(dst_spacing, dtype=np.float64))
+    off = a @ (np.asarray(dst_origin, dtype=np.float64) - np.asarray(src_origin, dtype=np.float64))
+    return np.ascontiguousarray(np.concatenate([lin, off[:, None]], axis=1).reshape(-1))
+
+
+def resample_linear(src, m, dst_shape, default=0.0, cast="float"):
+    """ResampleImages / ResampleImagesFloat / AddImages' resampling (ITK linear, identity transform)."""
+    src = _c64(src)
+    m = _c64(m)
+    out = np.empty(tuple(int(v) for v in dst_shape), dtype=np.float64)
+    _load().oracle_resample_linear(_p(src), *src.shape, _p(m), _p(out), *out.shape, float(default),
+                                   1 if cast == "short" else 0)
+    return out
+
+
+def rescale_intensity(img, out_min=0.0, out_max=1.0):
+    img = _c64(img)
+    out = np.empty_like(img)
+    _load().oracle_rescale_intensity(_p(img), img.size, float(out_min), float(out_max), _p(out))
+    return out
+
+
+def plahe(img, radius=5, alpha=0.5, beta=0.5):
+    """itk::AdaptiveHistogramEqualizationImageFilter (AdaptiveHistogramMatch.cxx:30-42)."""
+    img = _c64(img)
+    out = np.empty_like(img)
+    _load().oracle_plahe(_p(img), *img.shape, int(radius), float(alpha), float(beta), _p(out))
+    return out

@@ -388,3 +388,132 @@ void oracle_sart_update(double *x, const double *upd, const double *invv, long n
             x[k * nyx + j] = val;
         }
 }
+
+/* ======================================================================================
+ * Artifact-Induction image operations: the ITK command-line
+ * tools of Physics-based-Augmentation/Artifact-Induction/Cpp-Codes, restated.  ITK itself
+ * is not vendored under /root/reference (the tools only #include it), so these follow the
+ * published behaviour of the ITK classes the tools instantiate: PARITY UNPINNED, anchored
+ * on the tools' own call sequences and on the known answers in
+ * tests/test_artifact_induction.py.
+ * Arrays are (Z,Y,X) C-order (X fastest), like the NRRD files the tools exchange.
+ * ====================================================================================== */
+
+/*
+ * itk::ResampleImageFilter + itk::LinearInterpolateImageFunction with the identity transform
+ * and default pixel value 0, as instantiated by ResampleImages.cxx:87-102,
+ * ResampleImagesFloat.cxx (same, float pixels), AddImages.cxx:40-53 and the iso-z branch of
+ * RescaleImage.cxx:44-92.
+ *   m[12]: continuous source index (x,y,z) of destination index (i,j,k):
+ *          cx = m[0] i + m[1] j + m[2] k + m[3], cy = m[4..7], cz = m[8..11]
+ *          (= Dsrc^-1 (Odst + Ddst diag(sdst) idx - Osrc) / ssrc, formed by the caller in double)
+ * Inside test: ITK's IsInsideBuffer on the continuous index, [-0.5, n-0.5) per axis.  Inside,
+ * LinearInterpolateImageFunction clamps: a base index below the first voxel is raised to it and
+ * the (then non-positive) distance means "no interpolation along this axis"; a neighbour past
+ * the last voxel is not read (the lower value is returned).  That is trilinear interpolation
+ * with edge clamping.  cast: 0 = float, 1 = short (ResampleImageFilter casts the double result
+ * with a bounds check and static_cast, i.e. truncation toward zero).
+ */
+void oracle_resample_linear(const double *src, long snz, long sny, long snx, const double *m,
+                            double *dst, long dnz, long dny, long dnx, double defval, int cast)
+{
+#pragma omp parallel for schedule(static) collapse(2)
+    for (long k = 0; k < dnz; ++k)
+        for (long j = 0; j < dny; ++j)
+            for (long i = 0; i < dnx; ++i) {
+                const double c[3] = {m[0] * i + m[1] * j + m[2] * k + m[3],
+                                     m[4] * i + m[5] * j + m[6] * k + m[7],
+                                     m[8] * i + m[9] * j + m[10] * k + m[11]};
+                const long n[3] = {snx, sny, snz};
+                double val = defval;
+                int inside = 1;
+                for (int a = 0; a < 3; ++a)
+                    if (!(c[a] >= -0.5 && c[a] < (double)n[a] - 0.5)) inside = 0;
+                if (inside) {
+                    long b[3], b1[3];
+                    double d[3];
+                    for (int a = 0; a < 3; ++a) {
+                        b[a] = (long)floor(c[a]);
+                        if (b[a] < 0) b[a] = 0;
+                        d[a] = c[a] - (double)b[a];
+                        if (d[a] < 0.0) d[a] = 0.0;
+                        b1[a] = b[a] + 1;
+                        if (b1[a] > n[a] - 1) { b1[a] = b[a]; }
+                    }
+                    double acc = 0.0;
+                    for (int dz = 0; dz < 2; ++dz)
+                        for (int dy = 0; dy < 2; ++dy)
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const double w = (dx ? d[0] : 1.0 - d[0]) * (dy ? d[1] : 1.0 - d[1]) *
+                                                 (dz ? d[2] : 1.0 - d[2]);
+                                acc += w * src[((dz ? b1[2] : b[2]) * sny + (dy ? b1[1] : b[1])) * snx +
+                                               (dx ? b1[0] : b[0])];
+                            }
+                    val = acc;
+                }
+                if (cast == 1) {
+                    if (val < -32768.0) val = -32768.0;
+                    if (val > 32767.0) val = 32767.0;
+                    val = (double)(short)val;             /* static_cast: toward zero */
+                }
+                dst[(k * dny + j) * dnx + i] = val;
+            }
+}
+
+/*
+ * itk::RescaleIntensityImageFilter (RescaleImage.cxx:99-104): out = (in + shift) * scale with
+ * scale = (outMax-outMin)/(inMax-inMin), shift = outMin/scale - inMin, clamped to [outMin,outMax];
+ * a constant image maps to outMin... ITK sets scale = 0 then, giving outMin.
+ */
+void oracle_rescale_intensity(const double *in, long n, double out_min, double out_max, double *out)
+{
+    double lo = in[0], hi = in[0];
+    for (long e = 1; e < n; ++e) { if (in[e] < lo) lo = in[e]; if (in[e] > hi) hi = in[e]; }
+    const double scale = (hi != lo) ? (out_max - out_min) / (hi - lo) : 0.0;
+    const double shift = (scale != 0.0) ? out_min / scale - lo : 0.0;
+#pragma omp parallel for schedule(static)
+    for (long e = 0; e < n; ++e) {
+        double v = (scale != 0.0) ? (in[e] + shift) * scale : out_min;
+        if (v < out_min) v = out_min;
+        if (v > out_max) v = out_max;
+        out[e] = v;
+    }
+}
+
+/*
+ * itk::AdaptiveHistogramEqualizationImageFilter (AdaptiveHistogramMatch.cxx:30-42; radius 5 and
+ * (alpha,beta) in {0,0.5,1}^2 per CBCT_pCT_Artifact_adding.sh:51-87): Stark's power-law adaptive
+ * histogram equalisation.  With u, v = intensities normalised to [-0.5,0.5] by the image min/max,
+ *   out = iscale * (0.5 + (1/N) sum_{v in window} F(u,v)) + min,
+ *   F(u,v) = 0.5 s |2(u-v)|^alpha - beta 0.5 s |2(u-v)| + beta u,   s = sgn(u-v) (0 at u == v),
+ * N = number of window voxels inside the image (the window is clipped at the border).
+ */
+void oracle_plahe(const double *in, long nz, long ny, long nx, long radius, double alpha, double beta,
+                  double *out)
+{
+    const long n = nz * ny * nx;
+    double lo = in[0], hi = in[0];
+    for (long e = 1; e < n; ++e) { if (in[e] < lo) lo = in[e]; if (in[e] > hi) hi = in[e]; }
+    const double iscale = hi - lo;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+    for (long k = 0; k < nz; ++k)
+        for (long j = 0; j < ny; ++j)
+            for (long i = 0; i < nx; ++i) {
+                const double u = (in[(k * ny + j) * nx + i] - lo) / iscale - 0.5;
+                const long k0 = k - radius < 0 ? 0 : k - radius, k1 = k + radius >= nz ? nz - 1 : k + radius;
+                const long j0 = j - radius < 0 ? 0 : j - radius, j1 = j + radius >= ny ? ny - 1 : j + radius;
+                const long i0 = i - radius < 0 ? 0 : i - radius, i1 = i + radius >= nx ? nx - 1 : i + radius;
+                double sum = 0.0;
+                for (long kk = k0; kk <= k1; ++kk)
+                    for (long jj = j0; jj <= j1; ++jj)
+                        for (long ii = i0; ii <= i1; ++ii) {
+                            const double v = (in[(kk * ny + jj) * nx + ii] - lo) / iscale - 0.5;
+                            const double d = u - v;
+                            const double s = d > 0.0 ? 1.0 : (d < 0.0 ? -1.0 : 0.0);
+                            const double ad = fabs(2.0 * d);
+                            sum += 0.5 * s * pow(ad, alpha) - beta * 0.5 * s * ad + beta * u;
+                        }
+                const double cnt = (double)((k1 - k0 + 1) * (j1 - j0 + 1) * (i1 - i0 + 1));
+                out[(k * ny + j) * nx + i] = iscale * (sum / cnt + 0.5) + lo;
+            }
+}

@@ -67,6 +67,14 @@ SYMBOLS = [
                                      ctypes.c_float, ctypes.c_float, _VP, _VP]),
     ("pax_compute_v", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_double, _VP, _VP]),
     ("pax_reduce_max", ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP]),
+    ("pax_resample_linear", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, _VP,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                           ctypes.c_int, _VP]),
+    ("pax_minmax", ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP]),
+    ("pax_rescale_intensity", ctypes.c_int, [_VP, ctypes.c_size_t, _VP, ctypes.c_double, ctypes.c_double,
+                                             _VP]),
+    ("pax_plahe", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_float, ctypes.c_float, _VP, _VP, _VP]),
     ("pax_ctnoise", ctypes.c_int, [_VP, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_uint64,
                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, _VP, ctypes.c_uint64,
                                    _VP]),
