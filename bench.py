@@ -41,6 +41,8 @@ def get_config(name):
 
 def describe(cfg, n_gpus, shard="angles"):
     geo = cfg["geo"]
+    if isinstance(shard, str):
+        shard = (n_gpus, 1)
     nsub = -(-len(cfg["angles"]) // cfg["blocksize"])
     return {
         "workload": f"{cfg['name']}: planning CT {int(geo.nVoxel[1])}x{int(geo.nVoxel[2])}x{int(geo.nVoxel[0])}, "
@@ -50,9 +52,8 @@ def describe(cfg, n_gpus, shard="angles"):
         "niter": cfg["niter"], "blocksize": cfg["blocksize"], "I0": cfg["I0"], "sigma": cfg["sigma"],
         "accuracy": float(geo.accuracy),
         "parallelism": "1 GPU" if n_gpus == 1 else (
-            f"angles of each subset interleaved over {n_gpus} GPUs" if shard == "angles" else
-            f"every angle of each subset, detector rows split in {n_gpus} bands (one per GPU; subsets of 20 "
-            f"do not divide by {n_gpus})") + ", volume replicated, NCCL all-reduce of the partial update per subset",
+            f"ranks in a {shard[0]} x {shard[1]} grid: the angles of each subset interleaved over {shard[0]} "
+            f"groups, the detector rows split in {shard[1]} bands") + ", volume replicated, NCCL all-reduce of the partial update per subset",
         "l2": "per-step working set (projections + volumes, ~2.4 GB at C2) exceeds the 126 MB L2; no flush",
     }
 
@@ -164,7 +165,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--shard", default="auto", choices=["auto", "angles", "rows"],
+    ap.add_argument("--shard", default="auto", choices=["auto", "grid", "angles", "rows"],
                     help="how a subset's rays are cut over the ranks (physics_arx_b200/dist.py)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -294,10 +295,10 @@ def main():
             "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": describe(cfg, world, pipe.st.shard),
+            "data": "synthetic", "config": describe(cfg, world, pipe.st.grid),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": ("k_ax_fan<4,2,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"
+                         "kernel": ("k_ax_fan<4,8,2,8,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"
                                     if pipe.plan.projector == "fan" else
                                     "k_ax<1,RESIDUAL,32> (ray-march projector, csrc/ax.cu)"),
                          "peak_source": peak_src, "avg_launch_ms": avg_ms,

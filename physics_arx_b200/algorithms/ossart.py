@@ -52,36 +52,36 @@ class OSSARTState:
         dev = proj.device if proj is not None else torch.device(
             "cuda", torch.cuda.current_device() if device is None else int(device))
         nv_full, nu = (int(v) for v in geo.nDetector)
-        self.shard = choose_shard(self.blocks, self.world, shard) if self.world > 1 else "angles"
-        if self.shard == "rows":
-            # every angle, a band of detector rows: the band is a detector of its own
-            self.v0, self.v1 = shard_rows(nv_full, self.rank, self.world)
-            local, self.ranges = shard_blocks(self.blocks, 0, 1)
-            empty = self.v1 <= self.v0
-            band = (0, 1) if empty else (self.v0, self.v1)      # keep a 1-row plan on an idle rank
-            plan_geo, plan_idx = row_window_geometry(geo, *band), local
-            if empty:
-                self.ranges = [(f, 0) for f, _ in self.ranges]
-        else:
-            self.v0, self.v1 = 0, nv_full
-            local, self.ranges = shard_blocks(self.blocks, self.rank, self.world)
-            # a rank may own no angle at all (n < world): keep one dummy angle so a plan exists
-            plan_idx = local if len(local) else np.array([0])
-            plan_geo = subset_geometry(geo, plan_idx, n)
+        # the ranks form an A x R grid: angles of every subset over A groups, detector rows over R bands
+        self.grid = choose_shard(self.blocks, self.world, shard) if self.world > 1 else (1, 1)
+        A, R = self.grid
+        self.shard = "angles" if R == 1 else ("rows" if A == 1 else "grid")
+        ra, rr = self.rank % A, self.rank // A
+        self.v0, self.v1 = shard_rows(nv_full, rr, R) if R > 1 else (0, nv_full)
+        local, self.ranges = shard_blocks(self.blocks, ra, A)
+        empty = self.v1 <= self.v0
+        band = (0, 1) if empty else (self.v0, self.v1)          # keep a 1-row plan on an idle rank
+        # a rank may own no angle at all (n < A): keep one dummy angle so a plan exists
+        plan_idx = local if len(local) else np.array([0])
+        plan_geo = subset_geometry(geo, plan_idx, n)
+        if R > 1:            # a band of detector rows is a detector of its own
+            plan_geo = row_window_geometry(plan_geo, *band)
+        if empty:
+            self.ranges = [(f, 0) for f, _ in self.ranges]
         self.local_idx = local
         self.plan = Plan(plan_geo, angles[plan_idx], device=dev.index)
         self.plan.w_geo = geo
-        n_own = len(local) if (self.shard == "angles" or self.v1 > self.v0) else 0
-        rows = self.v1 - self.v0 if self.shard == "rows" else nv_full
+        n_own = len(local) if self.v1 > self.v0 else 0
+        rows = self.v1 - self.v0
+        full_rows = rows == nv_full
         if proj is None:                                    # caller fills the rank-local buffer
             self.b = torch.empty((max(n_own, 1), max(rows, 1), nu), dtype=torch.float32,
                                  device=dev)[:n_own]
-        elif self.shard == "rows":
-            self.b = proj[:, self.v0:self.v1, :].contiguous()
-        elif len(local) == n and np.array_equal(local, np.arange(n)):
+        elif len(local) == n and full_rows and np.array_equal(local, np.arange(n)):
             self.b = proj                                   # ordered, single rank: no copy
         else:
-            self.b = proj[torch.as_tensor(local, device=dev, dtype=torch.long)].contiguous()
+            sel = proj[torch.as_tensor(local, device=dev, dtype=torch.long)] if n_own else proj[:0]
+            self.b = sel[:, self.v0:self.v1, :].contiguous()
         # V_s (A.5): a sum over the subset's angles, so partial sums all-reduce exactly
         p = self.plan
         V = torch.zeros((len(self.blocks), p.ny, p.nx), dtype=torch.float32, device=dev)

@@ -8,7 +8,8 @@ updates (and the partial V maps) add up exactly:
             band of a detector is itself a (shorter, V-shifted) detector, so nothing below the
             geometry bag changes; bilinear interpolation across a band boundary splits into two
             ramps that sum to one.  Balanced for any rank count (20 angles over 8 ranks are not).
-  'auto'    'angles' when every subset divides evenly, else 'rows'."""
+  'grid'    both at once: the ranks form an A x R grid (choose_shard); 'auto' picks the grid that gives
+            every rank the same number of angles per subset."""
 from __future__ import annotations
 
 import numpy as np
@@ -78,13 +79,29 @@ def row_window_geometry(geo, v0, v1, n_angles=None):
 
 
 def choose_shard(blocks, world, shard="auto"):
-    if shard in ("angles", "rows"):
-        return shard
-    if shard != "auto":
+    """(A, R): the ranks form an A x R grid -- the angles of every subset are interleaved over A groups and
+    every group splits the detector rows into R bands; rank r sits at (r % A, r // A).
+
+      'angles' -> (world, 1)   the prescribed scheme
+      'rows'   -> (1, world)
+      'grid' / 'auto' -> A = gcd(world, every subset's size), R = world / A: every rank gets the same
+                number of angles in every subset, and the row bands stay as tall as possible (the
+                fan-plane projector shares its work along detector columns).  Blocksize 20 with a tail
+                of 16 over 8 ranks gives 4 x 2: 5 (4) angles x half the rows per rank, instead of 3,3,3,3,
+                2,2,2,2 whole projections.  Measured at C2 on 8 x B200 (r1): see DESIGN.md section 6.
+    """
+    if isinstance(shard, (tuple, list)):                    # an explicit grid
+        a, r = (int(v) for v in shard)
+        if a < 1 or r < 1 or a * r != world:
+            raise ValueError(f"grid {shard} does not have {world} ranks")
+        return a, r
+    if shard == "angles":
+        return world, 1
+    if shard == "rows":
+        return 1, world
+    if shard not in ("auto", "grid"):
         raise ValueError(f"unknown shard mode {shard!r}")
-    # Row bands balance perfectly but shorten the detector columns the fan-plane projector shares its
-    # work over; measured at C2 on 8 x B200 (r1, fan-plane kernel): angles 1.44 s, rows 1.55 s per volume
-    # (with the ray-march kernel it was the other way round: 2.51 s vs 2.21 s).  Rows only when a rank
-    # would otherwise sit idle for whole subsets.
-    smallest = min(len(b) for b in blocks)
-    return "angles" if smallest >= world else "rows"
+    a = world
+    for b in blocks:
+        a = int(np.gcd(a, len(b)))
+    return a, world // a

@@ -80,21 +80,18 @@ class SCBCTPipeline:
         nv_full = int(np.asarray(self.geo.nDetector)[0])
         npix = nv_full * nu
         lib = p.lib
+        rows = st.v1 - st.v0
+        inner = 0 if rows == nv_full else rows * nu      # a band of rows: [angles][rows*nu] cut out of [angles][npix]
         with torch.cuda.device(self.device):
-            if st.shard == "rows":          # (N, rows, U) band of every angle
-                if self.n_local:
-                    _lib.check(lib.pax_ctnoise(_ptr(st.b), st.b.numel(), ctypes.c_uint64(st.v0 * nu),
-                                               (st.v1 - st.v0) * nu, ctypes.c_uint64(npix), self.I0, 0.0,
+            pos = 0
+            if self.n_local:
+                for g0, cnt in _contiguous_runs(self.local_idx):      # runs of consecutive global angles
+                    view = st.b[pos:pos + cnt]
+                    _lib.check(lib.pax_ctnoise(_ptr(view), view.numel(),
+                                               ctypes.c_uint64(int(g0) * npix + st.v0 * nu), inner,
+                                               ctypes.c_uint64(npix if inner else 0), self.I0, 0.0,
                                                self.sigma, _ptr(m), ctypes.c_uint64(self.seed), _stream()),
                                "pax_ctnoise")
-                    self.launches += 1
-            else:                           # whole projections of this rank's angles
-                pos = 0
-                for g0, cnt in _contiguous_runs(self.local_idx):
-                    view = st.b[pos:pos + cnt]
-                    _lib.check(lib.pax_ctnoise(_ptr(view), view.numel(), ctypes.c_uint64(int(g0) * npix), 0,
-                                               0, self.I0, 0.0, self.sigma, _ptr(m),
-                                               ctypes.c_uint64(self.seed), _stream()), "pax_ctnoise")
                     self.launches += 1
                     pos += cnt
         return st.b

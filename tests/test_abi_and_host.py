@@ -190,10 +190,13 @@ def test_choose_shard_auto():
     from physics_arx_b200 import order_subsets
     from physics_arx_b200.dist import choose_shard
     blocks = order_subsets(656, 20)                      # 32 x 20 + 16
-    assert choose_shard(blocks, 2) == "angles" and choose_shard(blocks, 4) == "angles"
-    assert choose_shard(blocks, 8) == "angles"           # 16- and 20-angle subsets keep 8 ranks busy
-    assert choose_shard(order_subsets(40, 6), 8) == "rows"   # a 4-angle tail would idle half the ranks
-    assert choose_shard(blocks, 8, "rows") == "rows"
+    assert choose_shard(blocks, 2) == (2, 1) and choose_shard(blocks, 4) == (4, 1)      # plain angle sharding
+    assert choose_shard(blocks, 8) == (4, 2)             # 5 (4) angles x half the rows on every rank
+    assert choose_shard(order_subsets(40, 7), 4) == (1, 4)   # 7 and 5 angles share no factor with 4: row bands
+    assert choose_shard(blocks, 8, "angles") == (8, 1) and choose_shard(blocks, 8, "rows") == (1, 8)
+    assert choose_shard(blocks, 8, (2, 4)) == (2, 4)
+    with pytest.raises(ValueError):
+        choose_shard(blocks, 8, (3, 2))
     with pytest.raises(ValueError):
         choose_shard(blocks, 2, "columns")
 

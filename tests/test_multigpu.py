@@ -32,8 +32,10 @@ def _worker(rank, world, port, q, shard):
     ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
     art = artifact_volume(geo.nVoxel, seed=1)
     kw = dict(niter=3, blocksize=5, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=3)
+    if shard == "grid":                     # 2 angle groups x (world/2) row bands
+        shard = (2, world // 2)
     pipe = SCBCTPipeline(geo, angles, group=dist.group.WORLD, shard=shard, **kw)
-    assert pipe.st.shard == shard
+    assert pipe.st.shard == (shard if isinstance(shard, str) else ("grid" if world > 2 else "angles"))
     sharded = pipe.run_host(ct, art).numpy().copy()
     ok, info = True, ""
     if rank == 0:
@@ -52,7 +54,7 @@ def _worker(rank, world, port, q, shard):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("shard", ["angles", "rows"])
+@pytest.mark.parametrize("shard", ["angles", "rows", "grid"])
 def test_sharded_pipeline_equals_single_gpu(shard):
     import torch
     n = torch.cuda.device_count()
