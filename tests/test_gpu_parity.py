@@ -294,3 +294,50 @@ def test_full_size_c2_projection_matches_oracle(oracle):
         assert plan.fault() == 0
         assert err <= PROJ_TOL, (kind, err)
         assert err <= 5e-6, (kind, err)
+
+
+@pytest.mark.parametrize("seed", list(range(14)))
+def test_fan_and_ray_kernels_agree_on_random_geometries(seed):
+    """Fuzz: random volume / detector sizes, spacings, offsets, distances and angles; the fan-plane kernel
+    (forced) against the ray-march kernel, which the float64 oracle pins on the fixed cases above."""
+    torch = _torch()
+    from physics_arx_b200 import _lib
+    from physics_arx_b200.phantom import make_geometry
+    from physics_arx_b200.projector import Plan
+    rng = np.random.default_rng(1000 + seed)
+    nvox = (int(rng.integers(6, 40)), int(rng.integers(12, 56)), int(rng.integers(12, 56)))
+    dvox = (float(rng.uniform(1.0, 6.0)), float(rng.uniform(0.8, 3.0)), float(rng.uniform(0.8, 3.0)))
+    ndet = (int(rng.integers(20, 400)), int(rng.integers(8, 40)))
+    ext_z = nvox[0] * dvox[0]
+    ddet = (float(rng.uniform(0.3, 1.6) * ext_z * 1.5 / ndet[0]), float(rng.uniform(1.0, 4.0)))
+    DSO = float(rng.uniform(500, 1200))
+    DSD = DSO + float(rng.uniform(300, 800))
+    off = (float(rng.uniform(-0.3, 0.3) * ndet[0] * ddet[0]), float(rng.uniform(-0.4, 0.4) * ndet[1] * ddet[1]))
+    geo = make_geometry(nvox, dvox, ndet, ddet, DSD=DSD, DSO=DSO, off_detector=off)
+    geo.offOrigin = np.array((rng.uniform(-0.2, 0.2) * ext_z, rng.uniform(-10, 10), rng.uniform(-10, 10)))
+    if seed % 3 == 0:
+        geo.accuracy = float(rng.choice([0.25, 0.4, 1.0]))
+    angles = np.sort(rng.uniform(0, 2 * np.pi, size=4))
+    if seed % 4 == 1:
+        angles[0] = 0.0
+        angles[1] = np.pi / 2          # axis-aligned views
+    plan = Plan(geo, angles)
+    if plan.fan_info()["rows_per_tile"] < 1:
+        with pytest.raises(ValueError):
+            plan.set_projector("fan")  # the kernel refuses geometries it cannot tile
+        return
+    vol = torch.from_numpy(rng.random(nvox).astype(np.float32)).cuda()
+    res = plan.pack(vol)
+    plan.set_projector("ray")
+    ns_r = torch.zeros(1, dtype=torch.int64, device="cuda")
+    pr = plan.ax(res, nsamples=ns_r)
+    plan.set_projector("fan")
+    ns_f = torch.zeros(1, dtype=torch.int64, device="cuda")
+    pf = plan.ax(res, nsamples=ns_f)
+    assert plan.fault() == 0, plan.fan_info()
+    den = float(pr.double().norm())
+    assert den > 0
+    err = float((pf - pr).double().norm()) / den
+    assert err <= 2e-5, (err, plan.fan_info())
+    assert float((pf - pr).abs().max()) <= 1e-3 * float(pr.max())
+    assert abs(int(ns_f.item()) - int(ns_r.item())) <= 2e-4 * int(ns_r.item()) + 4 * pr.numel() // len(angles)
