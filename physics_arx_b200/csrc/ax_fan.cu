@@ -22,20 +22,24 @@
 // re-associated; only fp32 rounding differs (measured ~1e-7 relative L2 against the float64 oracle).
 //
 // Kernel shape (sm_100a, no tensor cores: this is a gather plus prefix sums).  Every WARP works on
-// its own detector column (one angle, one u, a tile of rows) with its own tables in shared memory;
+// its own detector column (one angle, one u, a tile of <= 256 rows) with its own tables in shared memory;
 // there is no CTA-wide barrier, so the gather-heavy and the table-heavy phases of different warps
-// overlap on an SM.  Per run of equal n the warp cuts the rows into pieces whose z extent fits its
-// lanes, and walks the chord in chunks of G*8 steps:
-//   phase 0  a lane prepares one or two steps: in-plane cell offset and the four bilinear weights
-//            (positions from double, so nothing accumulates along the ray);
-//   phase 1  the warp advances G streams of 8 consecutive steps at once; a lane owns one stream and
-//            four consecutive slices of the chunk's z window (the resident volume is z-fastest, so a
-//            corner of a step is one 16-byte load per lane), accumulates P and Q down its stream and
-//            writes them to the table; a shuffle scan over the streams gives each its carry;
-//   phase 2  a lane owns up to RPL detector rows of the piece and adds up their stretches from the
-//            table (+ carry).
-// The z window of a chunk (rows of the piece x its steps) must fit the 4*LQ slices the lanes of a
-// stream cover; pax_fan_configure derives the piece size from the geometry so that it always does.
+// overlap on an SM.  Per run of equal n the warp walks the chord in chunks of G*8 steps:
+//   phase 0  once per chunk: a lane prepares one or two steps -- in-plane cell offset and the four
+//            bilinear weights (chunk origin split into integer cell + fraction in double, steps added
+//            in fp32, so nothing accumulates along the ray);
+//   groups   the rows of the run are cut, for THIS chunk, into groups whose z extent over the chunk fits
+//            the 4*LQ slices the lanes of a stream cover (closed form: z is linear in row and step);
+//   phase 1  per group: the warp advances G streams of 8 consecutive steps at once; a lane owns one
+//            stream and four consecutive slices of the group's z window (the resident volume is
+//            z-fastest, so a corner of a step is one 16-byte load per lane), accumulates P and Q down
+//            its stream and writes them to the table; a shuffle scan over the streams gives each its
+//            carry.  Loads are predicated (same cell: no load) and issued two steps ahead into two
+//            alternating register sets;
+//   phase 2  per group: a lane owns two detector rows at a time and adds up their stretches from the
+//            table (+ carry); the rows' running sums live in shared memory across chunks.
+// pax_fan_configure checks from the geometry that at least one row always fits (else the kernel is not
+// offered) and estimates how many do (AUTO's criterion).
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -296,7 +300,7 @@ struct FanRow {
     }
 };
 
-template <int LQ, int SB, int RPL, int NWARPS, int MODE>
+template <int LQ, int SB, int NWARPS, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
 {
     using Cfg = FanCfg<LQ, SB>;
@@ -515,18 +519,16 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
 // Piece size (rows) for which every chunk's z window fits the lanes, per kernel configuration, and
 // the mean length of the equal-n runs (what the sharing is worth).  All from the plan's geometry.
 template <int LQ, int SB>
-static int fan_piece_rows(const PaxGeo &g, double vz, double tau, double slope, int rpl)
+static int fan_piece_rows(const PaxGeo &g, double vz, double tau, double slope)
 {
     // window of a chunk <= rows*vz*tau (spread of the rows) + steps*slope (travel) + 2 (floor, +1)
     //                      + 3 (alignment to a quad) + slack  must fit W slices
     const double room = (double)FanCfg<LQ, SB>::W - 5.3 - FanCfg<LQ, SB>::CW * slope;
     int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
-    rows = std::max(0, std::min(rows, std::min(32 * rpl, (int)g.nDetecV)));
+    rows = std::max(0, std::min(rows, std::min(FAN_GROUP, (int)g.nDetecV)));
     return rows >= 32 ? rows / 32 * 32 : rows;      // whole warps of rows: no idle lanes in phase 2
 }
 
-#define FAN_RPL4 2
-#define FAN_RPL8 4
 #define FAN_NW8 5            // W=32 tables are twice as large: five warps per CTA, two CTAs per SM
 
 int pax_fan_configure(PaxPlan *p)
@@ -545,8 +547,8 @@ int pax_fan_configure(PaxPlan *p)
         const double za = std::fabs(A.oz - A.sz), zb = std::fabs(A.oz + (g.nDetecV - 1) * A.vz - A.sz);
         slope = std::fmax(slope, std::fmax(za, zb) / nmin);
     }
-    const int p4 = fan_piece_rows<4, 8>(g, vz, tau, slope, FAN_RPL4);
-    const int p8 = fan_piece_rows<8, 16>(g, vz, tau, slope, FAN_RPL8);
+    const int p4 = fan_piece_rows<4, 8>(g, vz, tau, slope);
+    const int p8 = fan_piece_rows<8, 16>(g, vz, tau, slope);
     // a W=32 chunk costs twice a W=16 chunk per step: take it when it carries more than twice the rows
     const char *force = getenv("PAX_FAN_LQ");                  // tuning hook
     int lq = (p8 > 3 * p4) ? 8 : 4;                             // (measured at C2: 12.1 ms vs 10.0 ms)
@@ -580,14 +582,14 @@ int pax_fan_configure(PaxPlan *p)
     return PAX_OK;
 }
 
-template <int LQ, int SB, int RPL, int NWARPS, int MODE>
+template <int LQ, int SB, int NWARPS, int MODE>
 static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
 {
     const size_t smem = sizeof(FanWarpSmem<LQ, SB>) * NWARPS;
-    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<LQ, SB, RPL, NWARPS, MODE>,
+    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<LQ, SB, NWARPS, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(pax_cdiv(a.nu, NWARPS), count, pax_cdiv(a.nv, a.fan_rows));
-    k_ax_fan<LQ, SB, RPL, NWARPS, MODE><<<grid, NWARPS * 32, smem, st>>>(a);
+    k_ax_fan<LQ, SB, NWARPS, MODE><<<grid, NWARPS * 32, smem, st>>>(a);
     return PAX_OK;
 }
 
@@ -607,8 +609,8 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
                                    "(the z window of a single detector row exceeds its lanes)");
     const bool plain = mode == PAX_AX_PLAIN;
     if (p->fan_lq == 8)
-        return plain ? fan_launch<8, 16, FAN_RPL8, FAN_NW8, PAX_AX_PLAIN>(a, count, st)
-                     : fan_launch<8, 16, FAN_RPL8, FAN_NW8, PAX_AX_RESIDUAL>(a, count, st);
-    return plain ? fan_launch<4, 8, FAN_RPL4, FAN_NW, PAX_AX_PLAIN>(a, count, st)
-                 : fan_launch<4, 8, FAN_RPL4, FAN_NW, PAX_AX_RESIDUAL>(a, count, st);
+        return plain ? fan_launch<8, 16, FAN_NW8, PAX_AX_PLAIN>(a, count, st)
+                     : fan_launch<8, 16, FAN_NW8, PAX_AX_RESIDUAL>(a, count, st);
+    return plain ? fan_launch<4, 8, FAN_NW, PAX_AX_PLAIN>(a, count, st)
+                 : fan_launch<4, 8, FAN_NW, PAX_AX_RESIDUAL>(a, count, st);
 }
