@@ -47,6 +47,9 @@
 #include "pax_internal.h"
 
 #define FAN_NW 8            // warps per CTA (independent; the CTA only groups adjacent columns for L1)
+#ifndef FAN_TWOSET
+#define FAN_TWOSET 0        // 1: two alternating corner register sets, loads two steps ahead (measured below)
+#endif
 #define FAN_GROUP 128       // most rows summed from one set of tables
 #define FAN_MAXTILE 256     // detector rows one warp walks (their sums and run-start masks live in smem)
 
@@ -173,6 +176,7 @@ __device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float 
             // one 64-bit add per step, the other corners are uniform strides away
             const char *bb = reinterpret_cast<const char *>(base);
             const size_t dx4 = (size_t)sxs * 4, dy4 = (size_t)sys * 4;
+#if FAN_TWOSET
             float4 d00 = c00, d01 = c00, d10 = c00, d11 = c00;           // the odd steps' set
             unsigned offE = op[0], offO = op[1];
             {
@@ -211,6 +215,42 @@ __device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float 
                 step(s, c00, c01, c10, c11, offE);
                 step(s + 1, d00, d01, d10, d11, offO);
             }
+#else
+            // one register set: the columns of step s+1 are requested right after step s consumed them
+            unsigned off = op[0];
+            {
+                const char *p00 = bb + off, *p10 = p00 + dy4;
+                fan_ld4_if(c00, p00, on); fan_ld4_if(c01, p00 + dx4, on);
+                fan_ld4_if(c10, p10, on); fan_ld4_if(c11, p10 + dx4, on);
+            }
+            float4 w = wp[0];
+    #pragma unroll
+            for (int s = 0; s < B; ++s) {
+                unsigned offn = off;
+                float4 wn = w;
+                if (s + 1 < B) { offn = op[s + 1]; wn = wp[s + 1]; }
+                const bool chg = on && offn != off;
+                const char *p00 = bb + offn, *p10 = p00 + dy4;
+                float2 v0 = fan_mul2(w.x, c00.x, c00.y), v1 = fan_mul2(w.x, c00.z, c00.w);
+                v0 = fan_fma2(w.y, c01.x, c01.y, v0); v1 = fan_fma2(w.y, c01.z, c01.w, v1);
+                v0 = fan_fma2(w.z, c10.x, c10.y, v0); v1 = fan_fma2(w.z, c10.z, c10.w, v1);
+                v0 = fan_fma2(w.w, c11.x, c11.y, v0); v1 = fan_fma2(w.w, c11.z, c11.w, v1);
+                if (s + 1 < B) {
+                    fan_ld4_if(c00, p00, chg); fan_ld4_if(c01, p00 + dx4, chg);
+                    fan_ld4_if(c10, p10, chg); fan_ld4_if(c11, p10 + dx4, chg);
+                }
+                pq0.x += v0.x; pq1.x += v0.y; pq2.x += v1.x; pq3.x += v1.y;
+                pq0.y = fmaf(jf, v0.x, pq0.y); pq1.y = fmaf(jf, v0.y, pq1.y);
+                pq2.y = fmaf(jf, v1.x, pq2.y); pq3.y = fmaf(jf, v1.y, pq3.y);
+                jf += 1.f;
+                if (on) {
+                    Tw[s * (TS / 2)] = make_float4(pq0.x, pq0.y, pq1.x, pq1.y);
+                    Tw[s * (TS / 2) + 1] = make_float4(pq2.x, pq2.y, pq3.x, pq3.y);
+                }
+                off = offn;
+                w = wn;
+            }
+#endif
         }
         // carry of a stream = totals of the earlier streams: inclusive scan over g, minus own
         float2 t0 = pq0, t1 = pq1, t2 = pq2, t3 = pq3;

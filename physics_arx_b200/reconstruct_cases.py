@@ -66,7 +66,7 @@ def pCT_CBCT_reconstruction(in_dir, niter=30, blocksize=20, n_angles=500, Poisso
     done = []
     for patient, caseID, infile in list_cases(in_dir):
         img = read_nrrd(infile)
-        vol = torch.from_numpy(np.ascontiguousarray(img.array, dtype=np.float32)).cuda()
+        vol = torch.from_numpy(np.array(img.array, dtype=np.float32, order='C')).cuda()
         geo = case_geometry(img.GetSize(), img.GetSpacing(), half_fan)
         angles = np.linspace(0, 2 * np.pi, n_angles)
         projections = Ax(vol, geo, angles, 'interpolated', gpuids=gpuids)
