@@ -298,7 +298,7 @@ def main():
             "data": "synthetic", "config": describe(cfg, world, pipe.st.grid),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": ("k_ax_fan<4,8,2,8,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"
+                         "kernel": ("k_ax_fan<4,8,8,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"
                                     if pipe.plan.projector == "fan" else
                                     "k_ax<1,RESIDUAL,32> (ray-march projector, csrc/ax.cu)"),
                          "peak_source": peak_src, "avg_launch_ms": avg_ms,
