@@ -58,6 +58,34 @@ def main():
         hi=O.ctnoise_add(pin, Poisson=1e8, Gaussian=np.array([0.0, 4.0]), seed=7, maxval=200.0),
         mid=O.ctnoise_add(pin, Poisson=1e4, Gaussian=np.array([1.0, 2.0]), seed=7, maxval=200.0),
         lo=O.ctnoise_add(pin, Poisson=300.0, Gaussian=np.array([0.0, 0.5]), seed=7, maxval=200.0, index0=1000))
+    # case 4: fan-plane regime (fine detector rows over thick slices, half-fan): Ax and a residual pass
+    geo = make_geometry((20, 36, 36), (2.5, 1.0, 1.0), (224, 56), (0.45, 1.5), off_detector=(0.0, -12.0))
+    angles = np.array([0.0, 0.7, 1.9, 3.3, 4.6, 5.8])
+    vol = rng.random((20, 36, 36)).astype(np.float32)
+    ax = O.ax(vol, geo, angles)
+    b = (ax * (1.0 + 0.1 * rng.standard_normal(ax.shape))).astype(np.float32)
+    w = O.compute_w(geo, angles, "matlab")
+    np.savez_compressed(os.path.join(HERE, "fan_ops.npz"), angles=angles, vol=vol, ax=ax, b=b,
+                        resid=w * (b.astype(np.float64) - ax), **geo_params(geo))
+    # case 5: artifact induction (CBCT_pCT_Artifact_adding.sh steps 1-4, one variation)
+    z, y, x = np.meshgrid(np.arange(10), np.arange(22), np.arange(26), indexing="ij")
+    pct = np.round(-800 + 900 * np.exp(-((x - 13) ** 2 + (y - 11) ** 2) / 60.0)
+                   + 40 * rng.standard_normal(x.shape)).astype(np.int16)
+    z, y, x = np.meshgrid(np.arange(24), np.arange(30), np.arange(28), indexing="ij")
+    cbct = np.round(-750 + 800 * np.exp(-((x - 14) ** 2 + (y - 16) ** 2) / 80.0)
+                    + 60 * rng.standard_normal(x.shape) + 3.0 * z).astype(np.int16)
+    pg = dict(spacing=(1.2, 1.2, 2.5), origin=(-15.0, -13.0, -12.0))
+    cg = dict(spacing=(1.0, 1.0, 1.0), origin=(-13.0, -16.0, -11.0))
+    m = O.index_map(pg["origin"], pg["spacing"], np.eye(3), cg["origin"], cg["spacing"], np.eye(3))
+    w1 = O.resample_linear(cbct.astype(np.float64), m, pct.shape, cast="short")
+    hist = O.plahe(w1, 5, 0.5, 0.5)
+    added = pct.astype(np.float64) + hist
+    nz = int(pct.shape[0] * 2.5 / 1.2)
+    m2 = O.index_map(pg["origin"], (1.2, 1.2, 1.2), np.eye(3), pg["origin"], pg["spacing"], np.eye(3))
+    rsc = O.rescale_intensity(O.resample_linear(added, m2, (nz,) + pct.shape[1:]), 0, 1)
+    np.savez_compressed(os.path.join(HERE, "artifact.npz"), pct=pct, cbct=cbct, pct_spacing=pg["spacing"],
+                        pct_origin=pg["origin"], cbct_spacing=cg["spacing"], cbct_origin=cg["origin"],
+                        cbct_w1=w1.astype(np.int16), hist=hist.astype(np.float32), rsc=rsc.astype(np.float32))
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -341,3 +341,24 @@ def test_fan_and_ray_kernels_agree_on_random_geometries(seed):
     assert err <= 2e-5, (err, plan.fan_info())
     assert float((pf - pr).abs().max()) <= 1e-3 * float(pr.max())
     assert abs(int(ns_f.item()) - int(ns_r.item())) <= 2e-4 * int(ns_r.item()) + 4 * pr.numel() // len(angles)
+
+
+def test_c1_like_pipeline_matches_oracle_after_five_iterations(oracle):
+    """BASELINE.json's C1 recipe at half size (64^3 @ 4 mm, 96 angles, 128x128 detector @ 4 mm, scatter +
+    noise, 5-iteration OS-SART with blocksize 20): the reconstructed volume within the stated tolerance of
+    the float64 oracle run through the same sequence."""
+    _torch()
+    from physics_arx_b200.phantom import artifact_volume, lung_phantom, make_geometry
+    from physics_arx_b200.pipeline import SCBCTPipeline
+    geo = make_geometry((64, 64, 64), (4.0, 4.0, 4.0), (128, 128), (4.0, 4.0))
+    angles = np.linspace(0, 2 * np.pi, 96)
+    ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    art = artifact_volume(geo.nVoxel, seed=1)
+    pipe = SCBCTPipeline(geo, angles, niter=5, blocksize=20, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=5)
+    got = pipe.run_host(ct, art).numpy()
+    p = oracle.ax(ct.astype(np.float64) + 0.5 * art.astype(np.float64), geo, angles)
+    p = oracle.ctnoise_add(p.astype(np.float32), Poisson=1e8, Gaussian=np.array([0.0, 4.0]), seed=5)
+    ref = oracle.ossart(p.astype(np.float32), geo, angles, 5, blocksize=20)
+    d = np.abs(got.astype(np.float64) - ref) * HU
+    assert d.mean() <= 1.0 and d.max() <= 5.0, (d.mean(), d.max())
+    assert d.mean() <= 0.01, d.mean()          # in practice three orders of magnitude inside the tolerance
