@@ -105,7 +105,6 @@ __device__ __forceinline__ void fan_slab(double s, double d, double lo, double h
     }
 }
 
-__device__ __forceinline__ void fan_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // predicated 16-byte read-only load: v keeps its value when `take` is false (no branch, so the load
 // can be issued a step ahead of its use)
 __device__ __forceinline__ void fan_ld4_if(float4 &v, const void *p, bool take)
@@ -128,11 +127,6 @@ __device__ __forceinline__ float2 fan_shfl_up2(float2 v, int d)
 {
     return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
 }
-__device__ __forceinline__ void fan_sel4(float4 &c, const float4 &n, bool take)
-{
-    c.x = take ? n.x : c.x; c.y = take ? n.y : c.y; c.z = take ? n.z : c.z; c.w = take ? n.w : c.w;
-}
-__device__ __forceinline__ float4 fan_ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 // inclusive running (P,Q) of chunk-local step i (i >= 0) at table columns c and c+1
 template <int LQ, int SB>
@@ -639,10 +633,6 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     a.fan_rows = p->fan_rows;
     a.fan_piece = p->fan_piece;
     a.fault = p->d_fault;
-    {
-        const char *ev = getenv("PAX_FAN_PREFETCH");            // tuning hook
-        a.fan_prefetch = ev ? atoi(ev) : 0;      // measured at C2: 12.3 ms with, 10.2 ms without (L1 is too small)
-    }
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
     PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
     PAX_REQUIRE(p->fan_piece >= 1, "pax_ax: the fan-plane projector does not fit this geometry "

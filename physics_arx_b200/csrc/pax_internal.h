@@ -72,7 +72,6 @@ struct AxArgs {
     float whx, why, whz, wthr;
     int fan_rows;                 // ax_fan.cu: detector rows one warp walks
     int fan_piece;                // ax_fan.cu: most rows that share one z window
-    int fan_prefetch;             // ax_fan.cu: prefetch the next chunk's columns into L1
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
     int *fault;                   // ax_fan.cu: set to 1 if a z window did not fit (never, by construction)
 };
