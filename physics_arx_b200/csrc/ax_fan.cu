@@ -47,9 +47,6 @@
 #include "pax_internal.h"
 
 #define FAN_NW 8            // warps per CTA (independent; the CTA only groups adjacent columns for L1)
-#ifndef FAN_TWOSET
-#define FAN_TWOSET 0        // 1: two alternating corner register sets, loads two steps ahead (measured below)
-#endif
 #define FAN_GROUP 128       // most rows summed from one set of tables
 #define FAN_MAXTILE 256     // detector rows one warp walks (their sums and run-start masks live in smem)
 
@@ -71,8 +68,8 @@ struct __align__(16) FanWarpSmem {
     float2 T[Cfg::TROWS * Cfg::TS];             // stream-local running (P,Q) per (step, slice)
     float2 carry[Cfg::G * Cfg::TS];             // (P,Q) of all earlier streams of the chunk
     float2 total[Cfg::TS];                      // (P,Q) of the whole chunk
-    float4 w[Cfg::TROWS];                       // bilinear weights per step (stream-padded)
-    unsigned off[Cfg::TROWS];                   // in-plane cell offset per step, bytes
+    float4 w[Cfg::TROWS];                       // per step (stream-padded): three bilinear weights (the fourth
+                                                // is 1 - their sum) and the in-plane cell's byte offset
     unsigned starts[FAN_MAXTILE / 32];          // bit r of word w: row 32w+r starts a run of equal n
     float rsum[FAN_MAXTILE];                    // running line integral of every row of the tile
 };
@@ -158,7 +155,6 @@ __device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float 
         float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
         const int row0 = g * (B + 1);             // table row of the stream's first step
         const float4 *wp = sm.w + row0;
-        const unsigned *op = sm.off + row0;
         float4 *Tw = reinterpret_cast<float4 *>(sm.T + row0 * TS + 4 * q);
         float jf = (float)(g * B - CW / 2);
         if (g * B < nst) {
@@ -170,65 +166,26 @@ __device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float 
             // one 64-bit add per step, the other corners are uniform strides away
             const char *bb = reinterpret_cast<const char *>(base);
             const size_t dx4 = (size_t)sxs * 4, dy4 = (size_t)sys * 4;
-#if FAN_TWOSET
-            float4 d00 = c00, d01 = c00, d10 = c00, d11 = c00;           // the odd steps' set
-            unsigned offE = op[0], offO = op[1];
-            {
-                const char *p00 = bb + offE, *p10 = p00 + dy4;
-                fan_ld4_if(c00, p00, on); fan_ld4_if(c01, p00 + dx4, on);
-                fan_ld4_if(c10, p10, on); fan_ld4_if(c11, p10 + dx4, on);
-                const char *q00 = bb + offO, *q10 = q00 + dy4;
-                fan_ld4_if(d00, q00, on); fan_ld4_if(d01, q00 + dx4, on);
-                fan_ld4_if(d10, q10, on); fan_ld4_if(d11, q10 + dx4, on);
-            }
-            auto step = [&](const int s, float4 &x00, float4 &x01, float4 &x10, float4 &x11, unsigned &offx) {
-                const float4 w = wp[s];
-                float2 v0 = fan_mul2(w.x, x00.x, x00.y), v1 = fan_mul2(w.x, x00.z, x00.w);
-                v0 = fan_fma2(w.y, x01.x, x01.y, v0); v1 = fan_fma2(w.y, x01.z, x01.w, v1);
-                v0 = fan_fma2(w.z, x10.x, x10.y, v0); v1 = fan_fma2(w.z, x10.z, x10.w, v1);
-                v0 = fan_fma2(w.w, x11.x, x11.y, v0); v1 = fan_fma2(w.w, x11.z, x11.w, v1);
-                if (s + 2 < B) {
-                    const unsigned offn = op[s + 2];
-                    const bool chg = on && offn != offx;
-                    const char *p00 = bb + offn, *p10 = p00 + dy4;
-                    fan_ld4_if(x00, p00, chg); fan_ld4_if(x01, p00 + dx4, chg);
-                    fan_ld4_if(x10, p10, chg); fan_ld4_if(x11, p10 + dx4, chg);
-                    offx = offn;
-                }
-                pq0.x += v0.x; pq1.x += v0.y; pq2.x += v1.x; pq3.x += v1.y;
-                pq0.y = fmaf(jf, v0.x, pq0.y); pq1.y = fmaf(jf, v0.y, pq1.y);
-                pq2.y = fmaf(jf, v1.x, pq2.y); pq3.y = fmaf(jf, v1.y, pq3.y);
-                jf += 1.f;
-                if (on) {
-                    Tw[s * (TS / 2)] = make_float4(pq0.x, pq0.y, pq1.x, pq1.y);
-                    Tw[s * (TS / 2) + 1] = make_float4(pq2.x, pq2.y, pq3.x, pq3.y);
-                }
-            };
-    #pragma unroll
-            for (int s = 0; s < B; s += 2) {
-                step(s, c00, c01, c10, c11, offE);
-                step(s + 1, d00, d01, d10, d11, offO);
-            }
-#else
             // one register set: the columns of step s+1 are requested right after step s consumed them
-            unsigned off = op[0];
+            float4 w = wp[0];
+            unsigned off = __float_as_uint(w.w);
             {
                 const char *p00 = bb + off, *p10 = p00 + dy4;
                 fan_ld4_if(c00, p00, on); fan_ld4_if(c01, p00 + dx4, on);
                 fan_ld4_if(c10, p10, on); fan_ld4_if(c11, p10 + dx4, on);
             }
-            float4 w = wp[0];
     #pragma unroll
             for (int s = 0; s < B; ++s) {
-                unsigned offn = off;
                 float4 wn = w;
-                if (s + 1 < B) { offn = op[s + 1]; wn = wp[s + 1]; }
+                if (s + 1 < B) wn = wp[s + 1];
+                const unsigned offn = __float_as_uint(wn.w);
                 const bool chg = on && offn != off;
+                const float w11 = 1.f - w.x - w.y - w.z;              // the weights sum to one
                 const char *p00 = bb + offn, *p10 = p00 + dy4;
                 float2 v0 = fan_mul2(w.x, c00.x, c00.y), v1 = fan_mul2(w.x, c00.z, c00.w);
                 v0 = fan_fma2(w.y, c01.x, c01.y, v0); v1 = fan_fma2(w.y, c01.z, c01.w, v1);
                 v0 = fan_fma2(w.z, c10.x, c10.y, v0); v1 = fan_fma2(w.z, c10.z, c10.w, v1);
-                v0 = fan_fma2(w.w, c11.x, c11.y, v0); v1 = fan_fma2(w.w, c11.z, c11.w, v1);
+                v0 = fan_fma2(w11, c11.x, c11.y, v0); v1 = fan_fma2(w11, c11.z, c11.w, v1);
                 if (s + 1 < B) {
                     fan_ld4_if(c00, p00, chg); fan_ld4_if(c01, p00 + dx4, chg);
                     fan_ld4_if(c10, p10, chg); fan_ld4_if(c11, p10 + dx4, chg);
@@ -244,7 +201,6 @@ __device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float 
                 off = offn;
                 w = wn;
             }
-#endif
         }
         // carry of a stream = totals of the earlier streams: inclusive scan over g, minus own
         float2 t0 = pq0, t1 = pq1, t2 = pq2, t3 = pq3;
@@ -426,8 +382,8 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
                     const float fddx = (float)ddx, fddy = (float)ddy;
 #pragma unroll
                     for (int t = lane; t < CW; t += 32) {
-                        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                        unsigned off = 0;
+                        // a step past the run's end reads the all-zero rim column (0,0) with weight one
+                        float4 w = make_float4(1.f, 0.f, 0.f, __uint_as_float(0u));
                         if (t < nst) {
                             const float px = fmaf((float)t, fddx, exf), py = fmaf((float)t, fddy, eyf);
                             const float flx = floorf(px), fly = floorf(py);
@@ -437,12 +393,11 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
                             // an ulp outside in fp32, and must then weigh the rim, not the next column
                             const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
                             const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
-                            off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
+                            const unsigned off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
                             const float gx = 1.f - fx, gy = 1.f - fy;
-                            w = make_float4(gx * gy, fx * gy, gx * fy, fx * fy);
+                            w = make_float4(gx * gy, fx * gy, gx * fy, __uint_as_float(off));
                         }
                         sm.w[t + (t >> LOGB)] = w;
-                        sm.off[t + (t >> LOGB)] = off;
                     }
                 }
                 // z of row r at the first / last step of the chunk: Aa + Ba r, Ab + Bb r  (Ba, Bb >= 0)
