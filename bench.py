@@ -296,6 +296,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": describe(cfg, world, pipe.st.grid),
+            "collective": (None if world == 1 else
+                           ("fused reduce + update + broadcast kernel over " + pipe.st.fused["kind"]
+                            if pipe.st.fused is not None else "NCCL all-reduce + local update kernel")),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": ("k_ax_fan<4,8,8,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"

@@ -149,6 +149,17 @@ int pax_atb(const PaxPlan *plan, const float *proj, int first, int count, float 
 int pax_sart_update(const PaxPlan *plan, float *x_res, const float *upd_res, const float *inv_v,
                     float lambda, int noneg, void *stream);
 
+/* The same update FUSED with its multi-GPU collective: every rank holds a partial update
+ * in a symmetric (peer-mapped) buffer; rank r of `world` reduces the r-th slice of the volume over all ranks,
+ * applies the update and writes the new x slice into every rank's iterate -- one kernel over NVLink peer
+ * memory instead of an all-reduce plus a local update.  Give either the multicast addresses of the two
+ * symmetric buffers (x_mc, upd_mc: NVSwitch multimem.ld_reduce / multimem.st) or the `world` peer pointers of
+ * each (x_peers, upd_peers: host arrays of device addresses).  The caller synchronises the ranks before (all
+ * partial updates complete) and after (all slices landed); every rank ends with bit-identical x. */
+int pax_sart_update_fused(const PaxPlan *plan, float *x_local, float *x_mc, const float *upd_mc,
+                          const uint64_t *x_peers, const uint64_t *upd_peers, int rank, int world,
+                          const float *inv_v, float lambda, int noneg, void *stream);
+
 /* IterativeReconAlg.set_w / set_v (A.5).  w_out (count,V,U); v_out (Y,X) = mean_z Atb_FDK(ones)
  * on the geometry with dVoxel scaled by vscale. */
 int pax_compute_w(const PaxPlan *plan, int first, int count, float half_z, float half_y,

@@ -63,6 +63,9 @@ SYMBOLS = [
     ("pax_atb", ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
                                ctypes.POINTER(PaxAtbEpilogue), _VP]),
     ("pax_sart_update", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_float, ctypes.c_int, _VP]),
+    ("pax_sart_update_fused", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_uint64),
+                                             ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, _VP,
+                                             ctypes.c_float, ctypes.c_int, _VP]),
     ("pax_compute_w", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_float, ctypes.c_float, _VP, _VP]),
     ("pax_compute_v", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_double, _VP, _VP]),

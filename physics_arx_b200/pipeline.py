@@ -48,7 +48,7 @@ class SCBCTPipeline:
         p = self.plan
         self.ct_res = p.new_volume()
         self.art_res = p.new_volume()
-        self.x_res = p.new_volume()
+        self.x_res = st.new_iterate()      # the symmetric buffer when the fused multi-GPU update is in use
         self.out = torch.empty((p.nz, p.ny, p.nx), dtype=torch.float32, device=self.device)
         self.launches = 0
         self._max = torch.zeros(1, dtype=torch.float32, device=self.device)

@@ -32,17 +32,30 @@ def _worker(rank, world, port, q, shard):
     ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
     art = artifact_volume(geo.nVoxel, seed=1)
     kw = dict(niter=3, blocksize=5, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=3)
+    want = "nccl"
+    if shard == "p2p":                      # the peer-pointer variant of the fused update kernel
+        os.environ["PAX_FUSED_UPDATE"] = "p2p"
+        shard, want = "angles", "peer pointers"
+    elif shard == "fused":                  # the fused kernel, multicast when the fabric has it
+        os.environ["PAX_FUSED_UPDATE"] = "1"
+        shard, want = "grid", "fused"
     if shard == "grid":                     # 2 angle groups x (world/2) row bands
         shard = (2, world // 2)
     pipe = SCBCTPipeline(geo, angles, group=dist.group.WORLD, shard=shard, **kw)
     assert pipe.st.shard == (shard if isinstance(shard, str) else ("grid" if world > 2 else "angles"))
     sharded = pipe.run_host(ct, art).numpy().copy()
+    coll = "nccl" if pipe.st.fused is None else pipe.st.fused["kind"]
+    if want == "fused":
+        assert pipe.st.fused is not None, getattr(pipe.st, "fused_error", "")
+    else:
+        assert coll == want, (coll, getattr(pipe.st, "fused_error", ""))
     ok, info = True, ""
     if rank == 0:
         single = SCBCTPipeline(geo, angles, **kw).run_host(ct, art).numpy()
         hu = np.abs(sharded - single) * 4095.0
         ok = bool(hu.mean() <= 0.05 and hu.max() <= 0.5)
-        info = f"mean {hu.mean():.2e} HU max {hu.max():.2e} HU"
+        info = f"mean {hu.mean():.2e} HU max {hu.max():.2e} HU, collective: {coll}, " \
+               f"{getattr(pipe.st, 'fused_error', '')}"
     # every rank must hold the same volume
     t = torch.from_numpy(sharded).cuda()
     ref = t.clone()
@@ -54,7 +67,7 @@ def _worker(rank, world, port, q, shard):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("shard", ["angles", "rows", "grid"])
+@pytest.mark.parametrize("shard", ["angles", "rows", "grid", "p2p", "fused"])
 def test_sharded_pipeline_equals_single_gpu(shard):
     import torch
     n = torch.cuda.device_count()
@@ -72,3 +85,4 @@ def test_sharded_pipeline_equals_single_gpu(shard):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
+    print(sorted(res)[0][2])
