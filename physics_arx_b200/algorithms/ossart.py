@@ -242,7 +242,8 @@ def ossart(proj, geo, angles, niter, **kwargs):
 
     kwargs: blocksize=20, lmbda=1, lmbda_red=0.99, OrderStrategy=None, init=None,
     noneg=True, verbose=False, computel2=False, gpuids=None; build extras: w_variant,
-    v_variant, group / distributed / shard (sharding over a torch.distributed group; dist.py).
+    v_variant, group / distributed / shard (sharding over a torch.distributed group; dist.py),
+    fused_update (the multi-GPU update as one kernel over symmetric memory; include/pax.h).
     Returns the (Z,Y,X) float32 volume (NumPy in -> NumPy out); with computel2 also the
     per-iteration ||b - Ax||_2.
     """
