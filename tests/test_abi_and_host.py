@@ -228,3 +228,26 @@ def test_row_band_is_a_detector_of_its_own(oracle):
     assert rel_l2(acc, full_atb) < 1e-12
     assert rel_l2(vacc, full_v) < 1e-12
     assert full_w.shape == (4, 22, 30)
+
+
+@pytest.mark.parametrize("world,nv,blocksize,n", [(8, 768, 20, 656), (4, 96, 6, 40), (6, 50, 9, 45), (2, 33, 5, 23)])
+def test_grid_sharding_covers_every_ray_once(world, nv, blocksize, n):
+    """(angle groups) x (row bands): over all ranks, every (angle, detector row) of every subset is owned
+    exactly once, and with the auto grid every rank gets the same number of angles in every subset."""
+    from physics_arx_b200 import order_subsets
+    from physics_arx_b200.dist import choose_shard, shard_blocks, shard_rows
+    blocks = order_subsets(n, blocksize)
+    A, R = choose_shard(blocks, world)
+    assert A * R == world
+    owned = np.zeros((n, nv), dtype=np.int32)
+    per_rank = []
+    for rank in range(world):
+        ra, rr = rank % A, rank // A
+        v0, v1 = shard_rows(nv, rr, R) if R > 1 else (0, nv)
+        local, ranges = shard_blocks(blocks, ra, A)
+        assert sum(c for _, c in ranges) == len(local)
+        per_rank.append([c for _, c in ranges])
+        owned[np.ix_(local, np.arange(v0, v1))] += 1
+    assert (owned == 1).all()
+    counts = np.array(per_rank)
+    assert (counts == counts[0]).all()          # equal angle counts per subset on every rank
