@@ -391,18 +391,7 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
         a.quad1 = vol_res1 ? reinterpret_cast<const char *>(q + per) : nullptr;
         a.qshift = qshift; a.nxq_f = (float)nxq;
         if (epi->mode == PAX_AX_RESIDUAL) {
-            const char *ev = getenv("PAX_AX_VARIANT");      // tuning hook (tools/profile_step.py)
-            switch (ev ? atoi(ev) : 0) {
-            case 1: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 4, 4>(a, count, st); break;
-            case 2: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 3, 8>(a, count, st); break;
-            case 3: launch_ax<1, PAX_AX_RESIDUAL, true, 4, 8, 4>(a, count, st); break;
-            case 4: launch_ax<1, PAX_AX_RESIDUAL, true, 4, 12, 4>(a, count, st); break;
-            case 5: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 5, 2>(a, count, st); break;
-            case 6: launch_ax<1, PAX_AX_RESIDUAL, true, 16, 2, 4>(a, count, st); break;
-            case 7: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 1, 4>(a, count, st); break;
-            case 8: launch_ax<1, PAX_AX_RESIDUAL, true, 8, 2, 8>(a, count, st); break;
-            default: launch_ax<1, PAX_AX_RESIDUAL, true>(a, count, st); break;
-            }
+            launch_ax<1, PAX_AX_RESIDUAL, true>(a, count, st);
         } else if (vol_res1) launch_ax<2, PAX_AX_PLAIN, true>(a, count, st);
         else launch_ax<1, PAX_AX_PLAIN, true>(a, count, st);
     } else {
