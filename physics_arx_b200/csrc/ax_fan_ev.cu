@@ -1,0 +1,602 @@
+// Fan-plane forward projector, event-driven (round 2): tigre.Ax 'interpolated' (reference call site
+// pCT_CBCT_Reconstruction.py:86 and, inside ossart, :103; algorithm SURVEY.md A.3) on TIGRE's own sample
+// lattice, with the in-plane half of the trilinear interpolation shared by all rays of a detector column
+// AND the rows touching the shared tables only when they cross a slice boundary.
+//
+// Sharing (as in ax_fan.cu).  The rays of a detector column u lie in one vertical plane through the source;
+// rows with equal n = ceil(|P-S|/accuracy) (a "run") share the in-plane sample positions, so
+//   sample(i, v) = (1-t) G_i(k) + t G_i(k+1),  k = floor(z_i(v)), t = z_i(v) - k,  G_i(k) = bilinear_xy(slice k).
+//
+// Events.  With running sums over the steps of an epoch,  A_k(j) = sum_{i<=j} G_i(k),
+// C_k(j) = sum_{i<=j} (i - ref) G_i(k), the sum of a row over the steps it spends in slice pair (k,k+1) is a
+// difference of  f_k(j) = A_k + tau_k (A_{k+1} - A_k) + s (C_{k+1} - C_k)   (tau_k = z_ref(v) - k, s = dz per step),
+// and the differences telescope: the line integral of row v over an epoch is
+//   f_K(last step)  -  sum over crossings of a boundary k at step j of  dir * (tau_k D2A_k(j-1) + s D2C_k(j-1)),
+//   D2X_k = X_{k-1} - 2 X_k + X_{k+1},  dir = +1 upwards.
+// A row costs one table look-up per slice-boundary crossing (~10 per ray at C2) and one per epoch, instead of
+// one trilinear sample per step (~1000) -- and, unlike ax_fan.cu, nothing per 64-step chunk.  The sums are
+// TIGRE's Riemann sum re-associated; only fp32 rounding differs (tools/fan_event_model.py: 2e-7 relative L2 at
+// epochs of 256 steps).
+//
+// "Row v is above boundary k at step i" is DEFINED as  v >= ceil(fma(a_k, rcp(i), -b)),  a_k = (k - sz) n / vz,
+// b = dz0 / vz.  It is monotone in i and in k by construction (correctly rounded operations are monotone),
+// so the crossings enumerated per boundary and the pair found at an epoch's end always agree; that it differs
+// from the exact predicate by ~1e-5 slices is harmless, the interpolant being continuous across a boundary.
+//
+// Kernel shape (sm_100a; a gather plus prefix sums, no tensor cores).  One WARP owns one detector column
+// (angle, u, up to FAN_MAXROWS rows).  A lane owns four consecutive slices (one 16-byte load per bilinear
+// corner: the resident volume is z-fastest) of one run; the lanes of a warp are packed, per epoch, with the
+// z ranges the runs of the column look at (greedy; what does not fit 32 lanes goes to a second pass).  Per step
+// a lane does 4 predicated LDG.128 (no load while the in-plane cell is unchanged), 8 packed FMAs for G, 4 packed
+// accumulates and 2 STS.128 of its running (A, C) into a ring of CW steps.  After every CW steps the lanes
+// enumerate the rows that crossed their boundaries (closed form: a row interval per boundary), and the warp
+// serves those events 32 at a time from the ring; at the end of an epoch every row reads its pair once.
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+
+#include "pax_internal.h"
+
+#define FAN_MAXSEG 8            // runs (pieces of runs) packed into the lanes of one pass
+#define FAN_QCAP 128            // crossing events served per round
+#define FAN_MAXROWS 1024        // detector rows one warp walks
+
+template <int CW>
+struct __align__(16) FanEvSmem {
+    float4 ring[CW * 64];                      // [step][half][lane]: (A0,A1,C0,C1) / (A2,A3,C2,C3) of the lane's quad
+    float4 w[FAN_MAXSEG][2 * CW + 1];          // per run and step (two windows): three bilinear weights + cell offset
+    float rtab[CW + 4];                        // rcp(step) of the window's steps (the crossing predicate)
+    unsigned queue[FAN_QCAP];
+    int s_ra[FAN_MAXSEG], s_rb[FAN_MAXSEG], s_base[FAN_MAXSEG], s_qa[FAN_MAXSEG], s_nq[FAN_MAXSEG];
+    int s_i0[FAN_MAXSEG], s_i1[FAN_MAXSEG], s_exc[FAN_MAXSEG], s_eyc[FAN_MAXSEG];
+    float s_nvz[FAN_MAXSEG], s_s0[FAN_MAXSEG], s_zvr[FAN_MAXSEG], s_zref0[FAN_MAXSEG], s_zrefv[FAN_MAXSEG];
+    float s_exf[FAN_MAXSEG], s_eyf[FAN_MAXSEG], s_fddx[FAN_MAXSEG], s_fddy[FAN_MAXSEG];
+    unsigned char lane_seg[32];
+    unsigned starts[FAN_MAXROWS / 32];         // bit r of word w: row 32w+r starts a run of equal n
+};
+
+// first row after `cur` that starts a new run (or nRows)
+__device__ __forceinline__ int fev_next_start(const unsigned *starts, int cur, int nRows)
+{
+    const int nw = (nRows + 31) >> 5;
+    int w = (cur + 1) >> 5;
+    if (w >= nw) return nRows;
+    unsigned bits = starts[w] & (0xffffffffu << ((cur + 1) & 31));
+    for (;;) {
+        if (bits) return min(nRows, w * 32 + __ffs(bits) - 1);
+        if (++w >= nw) return nRows;
+        bits = starts[w];
+    }
+}
+
+// range of the chord parameter lambda in [0,1] with s + lambda*d inside [lo, hi)
+__device__ __forceinline__ void fev_slab(double s, double d, double lo, double hi, double &t0, double &t1, bool &hit)
+{
+    if (d == 0.0) {
+        hit = hit && (s >= lo && s < hi);
+    } else {
+        const double r = 1.0 / d;
+        const double ta = (lo - s) * r, tb = (hi - s) * r;
+        t0 = fmax(t0, fmin(ta, tb));
+        t1 = fmin(t1, fmax(ta, tb));
+    }
+}
+
+__device__ __forceinline__ void fev_ld4_if(float4 &v, const void *p, bool take)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                 : "r"((int)take), "l"(p));
+}
+__device__ __forceinline__ float2 fev_mul2(float w, float a, float b)
+{
+    return __fmul2_rn(make_float2(w, w), make_float2(a, b));
+}
+__device__ __forceinline__ float2 fev_fma2(float w, float a, float b, float2 acc)
+{
+    return __ffma2_rn(make_float2(w, w), make_float2(a, b), acc);
+}
+
+// THE crossing predicate: first row that is above boundary k at the step whose reciprocal is r
+// (a = (k - sz) n / vz, b = dz0 / vz).  Every use goes through this function, bit for bit.
+__device__ __forceinline__ int fev_cv(float a, float r, float b)
+{
+    const float x = fminf(fmaxf(__fmaf_rn(a, r, -b), -1.0e6f), 1.0e6f);
+    return (int)ceilf(x);
+}
+__device__ __forceinline__ float fev_ak(int k, float szf, float nvz)
+{
+    return __fmul_rn(__fsub_rn((float)k, szf), nvz);
+}
+__device__ __forceinline__ float fev_rcp_step(int i)
+{
+    return i > 0 ? __frcp_rn((float)i) : 2.0f;             // decreasing in i, finite at the source
+}
+
+template <int CW, int NWARPS, int MODE>
+__global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
+{
+    extern __shared__ __align__(16) unsigned char fev_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows_pad = (a.fan_rows + 3) & ~3;
+    const size_t per_warp = sizeof(FanEvSmem<CW>) + (size_t)rows_pad * sizeof(float);
+    FanEvSmem<CW> &sm = *reinterpret_cast<FanEvSmem<CW> *>(fev_smem_raw + (size_t)warp * per_warp);
+    float *rsum = reinterpret_cast<float *>(&sm + 1);             // running line integral of every row of the band
+
+    const int u = blockIdx.x * NWARPS + warp;
+    if (u >= a.nu) return;                                        // warps are independent: no CTA barriers below
+    const int ia = blockIdx.y;
+    const int V0 = blockIdx.z * a.fan_rows;
+    const int nRows = min(a.fan_rows, a.nv - V0);
+    const AngleDev &A = a.angles[a.first + ia];
+    const double sx = A.sx, sy = A.sy, sz = A.sz;
+    const int kmin = (int)a.loz, kmax = (int)a.hiz;               // slices a sample can touch: [kmin, kmax]
+    const int xmaxc = (int)a.hix - 1, ymaxc = (int)a.hiy - 1;    // last in-plane cell whose +1 neighbour exists
+    const float szf = (float)sz;
+    const double dx = A.ox + u * A.ux - sx, dy = A.oy + u * A.uy - sy;
+    const double dxy2 = dx * dx + dy * dy;
+    const double racc = 1.0 / a.acc;
+    const double vz = A.vz;
+    const double dz0 = A.oz + (double)V0 * vz - sz;               // P_z - S_z of the band's row 0; +vz per row
+    const float bq = (float)(dz0 / vz);                           // the predicate's b
+    const int EP = a.fan_epoch;
+    const size_t dx4 = (size_t)a.nzp * 4, dy4 = (size_t)a.nxp * a.nzp * 4;
+    float r2 = 0.f, mymax = -INFINITY;
+    unsigned my_ns = 0;
+
+    // ---- runs of rows with equal n (TIGRE's lattice); clear the rows' sums
+    int nlo = INT_MAX, nhi = 0;
+    {
+        int last = -2;
+        for (int r0 = 0; r0 < nRows; r0 += 32) {
+            const bool in = r0 + lane < nRows;
+            const double dz = dz0 + (double)(r0 + lane) * vz;
+            const int n = in ? (int)ceil(sqrt(dxy2 + dz * dz) * racc) : -1;
+            if (in) { nlo = min(nlo, n); nhi = max(nhi, n); rsum[r0 + lane] = 0.f; }
+            int prev = __shfl_up_sync(0xffffffffu, n, 1);
+            if (lane == 0) prev = last;
+            const unsigned m = __ballot_sync(0xffffffffu, in && n != prev);
+            if (lane == 0) sm.starts[r0 >> 5] = m;
+            last = __shfl_sync(0xffffffffu, n, 31);
+        }
+        nlo = __reduce_min_sync(0xffffffffu, nlo);
+        nhi = __reduce_max_sync(0xffffffffu, nhi);
+        __syncwarp();
+    }
+
+    // ---- the chord's part inside the volume in x and y, as a range of lambda = i / n (all runs share it)
+    double lam0 = 0.0, lam1 = 1.0;
+    bool hit = true;
+    fev_slab(sx, dx, 0.0, (double)a.hix, lam0, lam1, hit);
+    fev_slab(sy, dy, 0.0, (double)a.hiy, lam0, lam1, hit);
+
+    if (hit && lam0 <= lam1) {
+        const int Emin = max((int)floor(lam0 * (double)nlo), 0), Emax = (int)ceil(lam1 * (double)nhi);
+#pragma unroll 1
+        for (int e0 = Emin; e0 <= Emax; e0 += EP) {
+            const int e1 = min(e0 + EP - 1, Emax);
+            const int ref = e0 + (EP >> 1);
+            const int nwin = (e1 - e0 + CW) / CW;
+            int cur = 0;
+#pragma unroll 1
+            while (cur < nRows) {
+                // ================= pack runs (or pieces of runs) into the lanes of one pass (uniform over the warp)
+                int nseg = 0, used = 0, rowA = -1, rowB = -1;
+#pragma unroll 1
+                while (cur < nRows && nseg < FAN_MAXSEG && used < 31) {
+                    const int e = fev_next_start(sm.starts, cur, nRows);
+                    const double dzc = dz0 + (double)cur * vz;
+                    const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
+                    const double rn = 1.0 / (double)nrun;
+                    const int I0 = max((int)ceil(lam0 * (double)nrun), 0), I1 = (int)floor(lam1 * (double)nrun);
+                    const int ja = max(I0, e0), jb = min(I1, e1);
+                    if (ja > jb) { cur = e; continue; }           // the run has no sample in this epoch
+                    const float s0f = (float)(dz0 * rn), zvrf = (float)(vz * rn);
+                    const float fa = (float)ja, fb = (float)jb;
+                    const float sA = fmaf((float)cur, zvrf, s0f);
+                    const float zlo = szf + fminf(fa * sA, fb * sA);
+                    const int ka = max(kmin, (int)floorf(fmaxf(zlo - 4e-3f, -1.0e6f)));
+                    if (ka > kmax) { cur = nRows; break; }        // this row and all above it look over the volume
+                    const int qa = ka >> 2, avail = 32 - used;
+                    // last row whose highest slice (+1 neighbour) still falls into the lanes left
+                    const float lim = (float)(4 * (qa + avail) - 1) - 8e-3f - szf;
+                    float rmaxf = (float)(e - 1);
+                    if (zvrf > 0.f) {
+                        if (fb > 0.f) rmaxf = fminf(rmaxf, (lim / fb - s0f) / zvrf - 1e-2f);
+                        if (fa > 0.f) rmaxf = fminf(rmaxf, (lim / fa - s0f) / zvrf - 1e-2f);
+                    }
+                    int rb = min(max((int)floorf(fmaxf(rmaxf, -1.0f)) + 1, cur + 1), e);
+                    int nq;
+                    for (;;) {
+                        const float sB = fmaf((float)(rb - 1), zvrf, s0f);
+                        const float zhi = szf + fmaxf(fa * sB, fb * sB);
+                        const int kb = max(min(kmax, (int)floorf(fminf(zhi + 4e-3f, 1.0e6f)) + 1), ka);
+                        nq = (kb >> 2) - qa + 1;
+                        if (nq <= avail || rb <= cur + 1) break;
+                        --rb;
+                    }
+                    if (nq > avail) {
+                        if (used > 0) break;                      // start a new pass with this run
+                        if (lane == 0 && a.fault) atomicExch(a.fault, 1);   // a single row does not fit: see pax_fan_configure
+                        nq = avail;
+                    }
+                    if (lane == 0) {
+                        const int g = nseg;
+                        sm.s_ra[g] = cur; sm.s_rb[g] = rb; sm.s_base[g] = used; sm.s_qa[g] = qa; sm.s_nq[g] = nq;
+                        sm.s_i0[g] = ja; sm.s_i1[g] = jb;
+                        sm.s_nvz[g] = (float)((double)nrun / vz);
+                        sm.s_s0[g] = s0f; sm.s_zvr[g] = zvrf;
+                        sm.s_zref0[g] = (float)(sz + (double)ref * dz0 * rn);
+                        sm.s_zrefv[g] = (float)((double)ref * vz * rn);
+                        // in-plane origin of the epoch, split in double into an integer cell and a fraction; steps
+                        // add t*d to the fraction in fp32 (t < EP): a position is good to a few 1e-6 voxels
+                        const double ddx = dx * rn, ddy = dy * rn;
+                        const double ex = sx + (double)e0 * ddx, ey = sy + (double)e0 * ddy;
+                        const double exi = floor(ex), eyi = floor(ey);
+                        sm.s_exc[g] = (int)exi; sm.s_eyc[g] = (int)eyi;
+                        sm.s_exf[g] = (float)(ex - exi); sm.s_eyf[g] = (float)(ey - eyi);
+                        sm.s_fddx[g] = (float)ddx; sm.s_fddy[g] = (float)ddy;
+                    }
+                    if (rowA < 0) rowA = cur;
+                    rowB = rb;
+                    used += nq;
+                    ++nseg;
+                    cur = rb;
+                }
+                if (nseg == 0) continue;
+                __syncwarp();
+
+                // ================= the pass
+                int myseg = -1;
+#pragma unroll 1
+                for (int g = 0; g < nseg; ++g)
+                    if (lane >= sm.s_base[g] && lane < sm.s_base[g] + sm.s_nq[g]) myseg = g;
+                const bool on = myseg >= 0;
+                const int sg = on ? myseg : 0;
+                const int quad = sm.s_qa[sg] + lane - sm.s_base[sg];
+                const int segra = sm.s_ra[sg], segrb = sm.s_rb[sg];
+                const int segjb = sm.s_i1[sg];                    // last step of my run in this epoch: no sample, hence
+                                                                  // no crossing to serve, after it
+                sm.lane_seg[lane] = (unsigned char)(on ? myseg : 255);
+                float ak0, ak1, ak2, ak3;
+                {
+                    const float nvz = sm.s_nvz[sg];
+                    ak0 = fev_ak(4 * quad + 0, szf, nvz); ak1 = fev_ak(4 * quad + 1, szf, nvz);
+                    ak2 = fev_ak(4 * quad + 2, szf, nvz); ak3 = fev_ak(4 * quad + 3, szf, nvz);
+                }
+                int cs0, cs1, cs2, cs3;                           // rows above my boundaries so far: [cs, segrb)
+                {
+                    const float r0 = fev_rcp_step(e0);
+                    cs0 = min(max(fev_cv(ak0, r0, bq), segra), segrb); cs1 = min(max(fev_cv(ak1, r0, bq), segra), segrb);
+                    cs2 = min(max(fev_cv(ak2, r0, bq), segra), segrb); cs3 = min(max(fev_cv(ak3, r0, bq), segra), segrb);
+                }
+                const char *bb = reinterpret_cast<const char *>(a.vol0 + 4 * (on ? quad : 0));
+                const float4 *wp = sm.w[sg];
+                float2 A01 = make_float2(0.f, 0.f), A23 = A01, C01 = A01, C23 = A01;
+                float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
+
+                // weights and cells of window m of the epoch (steps e0 + m CW ...), all runs of the pass
+                auto fill_w = [&](int m) {
+                    const int w0 = e0 + m * CW, half = (m & 1) * CW;
+                    for (int q = lane; q < nseg * CW; q += 32) {
+                        const int g = q / CW, t = q - g * CW, i = w0 + t;
+                        // a step outside the run's range reads the all-zero rim column (0,0) with weight one
+                        float4 w = make_float4(1.f, 0.f, 0.f, __uint_as_float(0u));
+                        if (i >= sm.s_i0[g] && i <= sm.s_i1[g]) {
+                            const int exc = sm.s_exc[g], eyc = sm.s_eyc[g];
+                            const float tf = (float)(i - e0);
+                            const float px = fmaf(tf, sm.s_fddx[g], sm.s_exf[g]), py = fmaf(tf, sm.s_fddy[g], sm.s_eyf[g]);
+                            const float flx = floorf(px), fly = floorf(py);
+                            const int cx = min(max(exc + (int)flx, 0), xmaxc);
+                            const int cy = min(max(eyc + (int)fly, 0), ymaxc);
+                            // fraction against the CLAMPED cell: a sample the double clip admitted may sit an ulp
+                            // outside in fp32, and must then weigh the rim, not the next column
+                            const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
+                            const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
+                            const unsigned off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
+                            const float gx = 1.f - fx, gy = 1.f - fy;
+                            w = make_float4(gx * gy, fx * gy, gx * fy, __uint_as_float(off));
+                        }
+                        sm.w[g][half + t] = w;
+                    }
+                };
+                fill_w(0);
+                __syncwarp();
+                float4 wv = wp[0];
+                unsigned off = __float_as_uint(wv.w);
+                {
+                    const char *p00 = bb + off, *p10 = p00 + dy4;
+                    fev_ld4_if(c00, p00, on); fev_ld4_if(c01, p00 + dx4, on);
+                    fev_ld4_if(c10, p10, on); fev_ld4_if(c11, p10 + dx4, on);
+                }
+                float jf = (float)(e0 - ref);
+#pragma unroll 1
+                for (int m = 0; m < nwin; ++m) {
+                    const int w0 = e0 + m * CW;
+                    fill_w(m + 1);                                // the next window (its first step is prefetched below)
+                    if (lane <= CW) sm.rtab[lane] = fev_rcp_step(w0 + lane);
+                    __syncwarp();
+                    // ---- CW steps: running (A, C) of my four slices into the ring
+                    {
+                        const int half = (m & 1) * CW;
+#pragma unroll
+                        for (int t = 0; t < CW; ++t) {
+                            const int tn = (t + 1 < CW) ? half + t + 1 : (half ^ CW);
+                            const float4 wn = wp[tn];
+                            const unsigned offn = __float_as_uint(wn.w);
+                            const bool chg = on && offn != off;
+                            const float w11 = 1.f - wv.x - wv.y - wv.z;          // the weights sum to one
+                            const char *p00 = bb + offn, *p10 = p00 + dy4;
+                            float2 v0 = fev_mul2(wv.x, c00.x, c00.y), v1 = fev_mul2(wv.x, c00.z, c00.w);
+                            v0 = fev_fma2(wv.y, c01.x, c01.y, v0); v1 = fev_fma2(wv.y, c01.z, c01.w, v1);
+                            v0 = fev_fma2(wv.z, c10.x, c10.y, v0); v1 = fev_fma2(wv.z, c10.z, c10.w, v1);
+                            v0 = fev_fma2(w11, c11.x, c11.y, v0); v1 = fev_fma2(w11, c11.z, c11.w, v1);
+                            // the columns of the next step, as soon as this one has consumed the registers
+                            fev_ld4_if(c00, p00, chg); fev_ld4_if(c01, p00 + dx4, chg);
+                            fev_ld4_if(c10, p10, chg); fev_ld4_if(c11, p10 + dx4, chg);
+                            A01 = __fadd2_rn(A01, v0); A23 = __fadd2_rn(A23, v1);
+                            C01 = __ffma2_rn(make_float2(jf, jf), v0, C01);
+                            C23 = __ffma2_rn(make_float2(jf, jf), v1, C23);
+                            jf += 1.f;
+                            sm.ring[t * 64 + lane] = make_float4(A01.x, A01.y, C01.x, C01.y);
+                            sm.ring[t * 64 + 32 + lane] = make_float4(A23.x, A23.y, C23.x, C23.y);
+                            off = offn;
+                            wv = wn;
+                        }
+                    }
+                    __syncwarp();
+                    // ---- crossings at steps w0+1 .. iend (prefix through the step before, i.e. ring row t-1)
+                    const int iend = min(w0 + CW, e1);
+                    int lo0, lo1, lo2, lo3, n0, n1, n2, n3;
+                    unsigned up = 0;
+                    {
+                        const int il = min(iend, segjb);
+                        int c0 = cs0, c1 = cs1, c2 = cs2, c3 = cs3;
+                        if (il > w0) {
+                            const float re = sm.rtab[il - w0];
+                            c0 = min(max(fev_cv(ak0, re, bq), segra), segrb); c1 = min(max(fev_cv(ak1, re, bq), segra), segrb);
+                            c2 = min(max(fev_cv(ak2, re, bq), segra), segrb); c3 = min(max(fev_cv(ak3, re, bq), segra), segrb);
+                        }
+                        lo0 = min(c0, cs0); n0 = on ? abs(c0 - cs0) : 0; up |= (c0 < cs0) ? 1u : 0u;
+                        lo1 = min(c1, cs1); n1 = on ? abs(c1 - cs1) : 0; up |= (c1 < cs1) ? 2u : 0u;
+                        lo2 = min(c2, cs2); n2 = on ? abs(c2 - cs2) : 0; up |= (c2 < cs2) ? 4u : 0u;
+                        lo3 = min(c3, cs3); n3 = on ? abs(c3 - cs3) : 0; up |= (c3 < cs3) ? 8u : 0u;
+                        cs0 = c0; cs1 = c1; cs2 = c2; cs3 = c3;
+                    }
+                    const int mine = n0 + n1 + n2 + n3;
+                    int incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll 1
+                    for (int qb = 0; qb < total; qb += FAN_QCAP) {
+                        // my events into the queue: (row, slot = 4*lane + slice, direction)
+                        {
+                            int idx = incl - mine - qb;
+                            const unsigned slot = (unsigned)(lane * 4) << 16;
+                            for (int r = 0; r < n0; ++r, ++idx)
+                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo0 + r) | slot | ((up & 1u) << 31);
+                            for (int r = 0; r < n1; ++r, ++idx)
+                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo1 + r) | (slot + (1u << 16)) | ((up & 2u) << 30);
+                            for (int r = 0; r < n2; ++r, ++idx)
+                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo2 + r) | (slot + (2u << 16)) | ((up & 4u) << 29);
+                            for (int r = 0; r < n3; ++r, ++idx)
+                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo3 + r) | (slot + (3u << 16)) | ((up & 8u) << 28);
+                        }
+                        __syncwarp();
+                        const int nev = min(FAN_QCAP, total - qb);
+                        for (int q = lane; q < nev; q += 32) {
+                            const unsigned ev = sm.queue[q];
+                            const int v = (int)(ev & 0xffffu), slot = (int)((ev >> 16) & 0x7fu);
+                            const bool isup = (ev >> 31) != 0;
+                            const int L = slot >> 2, s = slot & 3;
+                            const int g = sm.lane_seg[L];
+                            const int base = sm.s_base[g], nq = sm.s_nq[g];
+                            const int k = 4 * (sm.s_qa[g] + L - base) + s;
+                            const float ak = fev_ak(k, szf, sm.s_nvz[g]);
+                            // first step of the window at which the row is on the new side (binary search on
+                            // the monotone predicate; at iend it is, at w0 it is not)
+                            int tl = 1, th = min(iend, sm.s_i1[g]) - w0;
+                            while (tl < th) {
+                                const int mid = (tl + th) >> 1;
+                                const bool above = v >= fev_cv(ak, sm.rtab[mid], bq);
+                                if (above == isup) th = mid; else tl = mid + 1;
+                            }
+                            const float4 *row = sm.ring + (tl - 1) * 64;
+                            const int pa = 2 * L + (s >> 1);              // my slice pair, and the one holding the
+                            const int pb = (s & 1) ? pa + 1 : pa - 1;     // neighbour on the other side
+                            const float4 P = row[(pa & 1) * 32 + (pa >> 1)];
+                            float4 Q = make_float4(0.f, 0.f, 0.f, 0.f);   // beyond the run's lanes: zero slices
+                            if (pb >= 2 * base && pb < 2 * (base + nq)) Q = row[(pb & 1) * 32 + (pb >> 1)];
+                            float d2a, d2c;
+                            if (s & 1) { d2a = P.x - 2.f * P.y + Q.x; d2c = P.z - 2.f * P.w + Q.z; }
+                            else       { d2a = Q.y - 2.f * P.x + P.y; d2c = Q.w - 2.f * P.z + P.w; }
+                            const float fv = (float)v;
+                            const float sv = fmaf(fv, sm.s_zvr[g], sm.s_s0[g]);
+                            const float tau = fmaf(fv, sm.s_zrefv[g], sm.s_zref0[g]) - (float)k;
+                            const float val = fmaf(tau, d2a, sv * d2c);
+                            atomicAdd(rsum + v, isup ? -val : val);
+                        }
+                        __syncwarp();
+                    }
+                }
+                // ---- end of the epoch: every row reads its slice pair once (prefix through step e1)
+                {
+                    const float4 *row = sm.ring + (e1 - (e0 + (nwin - 1) * CW)) * 64;
+#pragma unroll 1
+                    for (int g = 0; g < nseg; ++g) {
+                        // the run's last step of the epoch; the sums do not change after it (G = 0)
+                        const float re = fev_rcp_step(sm.s_i1[g]), fe = (float)sm.s_i1[g];
+                        const int base = sm.s_base[g], nq = sm.s_nq[g], k0 = 4 * sm.s_qa[g];
+                        const float nvz = sm.s_nvz[g], s0f = sm.s_s0[g], zvrf = sm.s_zvr[g];
+                        const float zr0 = sm.s_zref0[g], zrv = sm.s_zrefv[g];
+                        for (int v = sm.s_ra[g] + lane; v < sm.s_rb[g]; v += 32) {
+                            const float fv = (float)v;
+                            const float sv = fmaf(fv, zvrf, s0f);
+                            int K = (int)floorf(fminf(fmaxf(fmaf(fe, sv, szf), -1.0e6f), 1.0e6f));
+                            // the pair the PREDICATE puts the row in (an ulp of z may disagree with it)
+                            if (v >= fev_cv(fev_ak(K + 1, szf, nvz), re, bq)) ++K;
+                            else if (v < fev_cv(fev_ak(K, szf, nvz), re, bq)) --K;
+                            const int kap = K - k0;
+                            if (kap >= 0 && kap + 1 < 4 * nq) {
+                                const int pa = 2 * base + (kap >> 1);
+                                const float4 P = row[(pa & 1) * 32 + (pa >> 1)];
+                                float aK, aK1, cK, cK1;
+                                if (kap & 1) {
+                                    const float4 Q = row[((pa + 1) & 1) * 32 + ((pa + 1) >> 1)];
+                                    aK = P.y; cK = P.w; aK1 = Q.x; cK1 = Q.z;
+                                } else {
+                                    aK = P.x; aK1 = P.y; cK = P.z; cK1 = P.w;
+                                }
+                                const float tau = fmaf(fv, zrv, zr0) - (float)K;
+                                rsum[v] += fmaf(sv, cK1 - cK, fmaf(tau, aK1 - aK, aK));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- epilogue, run by run (the step length in mm depends on n).  The warps of the CTA own adjacent columns and
+    // fill one 32-byte sector of every row between them; L2 merges the partial writes.
+    int cur = 0;
+    while (cur < nRows) {
+        const int e = fev_next_start(sm.starts, cur, nRows);
+        const double dzc = dz0 + (double)cur * vz;
+        const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
+        const double rn = 1.0 / (double)nrun;
+        const double ddx = dx * rn, ddy = dy * rn;
+        double t0 = 0.0, t1 = (double)nrun;
+        bool hitr = true;
+        if (a.nsamples) {
+            fev_slab(sx, ddx, 0.0, (double)a.hix, t0, t1, hitr);
+            fev_slab(sy, ddy, 0.0, (double)a.hiy, t0, t1, hitr);
+        }
+        for (int r = cur + lane; r < e; r += 32) {
+            const int v = V0 + r;
+            const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
+            const double mx = ddx * a.dX, my = ddy * a.dY, mz = (dz0 + (double)r * vz) * rn * a.dZ;
+            const float p0 = rsum[r] * (float)sqrt(mx * mx + my * my + mz * mz);
+            if (a.nsamples) {                                     // exact count of the samples inside the open box
+                double tz0 = t0, tz1 = t1;
+                bool hz = hitr;
+                fev_slab(sz, (dz0 + (double)r * vz) * rn, (double)a.loz, (double)a.hiz, tz0, tz1, hz);
+                if (hz && tz0 <= tz1) {
+                    const int i0 = (int)ceil(tz0), i1 = (int)floor(tz1);
+                    if (i0 <= i1) my_ns += (unsigned)(i1 - i0 + 1);
+                }
+            }
+            if (MODE == PAX_AX_PLAIN) {
+                float val = a.a0 * p0;
+                if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
+                if (a.accumulate) val += a.out[o];
+                a.out[o] = val;
+                mymax = fmaxf(mymax, val);
+            } else {
+                const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
+                const float w = L > a.wthr ? 1.f / L : 0.f;
+                const float r_ = __ldg(a.b + o) - p0;
+                r2 = fmaf(r_, r_, r2);
+                a.out[o] = w * r_;
+            }
+        }
+        cur = e;
+    }
+    if (a.nsamples) {
+        const unsigned t = __reduce_add_sync(0xffffffffu, my_ns);
+        if (lane == 0 && t) atomicAdd(a.nsamples, (unsigned long long)t);
+    }
+    if (MODE == PAX_AX_PLAIN && a.maxout) {
+        for (int o = 16; o; o >>= 1) mymax = fmaxf(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+        if (lane == 0 && mymax > -INFINITY) {
+            const unsigned b = __float_as_uint(mymax);
+            atomicMax(a.maxout, (b & 0x80000000u) ? ~b : (b | 0x80000000u));
+        }
+    }
+    if (MODE == PAX_AX_RESIDUAL && a.sumsq) {
+        for (int o = 16; o; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        if (lane == 0) atomicAdd(a.sumsq, (double)r2);
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+template <int CW, int NWARPS, int MODE>
+static int fev_launch(const AxArgs &a, int count, cudaStream_t st)
+{
+    const size_t per_warp = sizeof(FanEvSmem<CW>) + (size_t)((a.fan_rows + 3) & ~3) * sizeof(float);
+    const size_t smem = per_warp * NWARPS;
+    PAX_REQUIRE(smem <= 227 * 1024, "pax_ax: fan-plane tables do not fit shared memory");
+    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan_ev<CW, NWARPS, MODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(pax_cdiv(a.nu, NWARPS), count, pax_cdiv(a.nv, a.fan_rows));
+    k_ax_fan_ev<CW, NWARPS, MODE><<<grid, NWARPS * 32, smem, st>>>(a);
+    return PAX_OK;
+}
+
+template <int CW, int NWARPS>
+static int fev_launch_mode(const AxArgs &a, int mode, int count, cudaStream_t st)
+{
+    return mode == PAX_AX_PLAIN ? fev_launch<CW, NWARPS, PAX_AX_PLAIN>(a, count, st)
+                                : fev_launch<CW, NWARPS, PAX_AX_RESIDUAL>(a, count, st);
+}
+
+int pax_ax_fan_ev_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, cudaStream_t st)
+{
+    AxArgs a = a0;
+    a.fan_rows = p->fev_rows;
+    a.fan_epoch = p->fev_epoch;
+    a.fault = p->d_fault;
+    PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
+    PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
+    PAX_REQUIRE(p->fev_epoch >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
+                                   "(the z travel of a single detector row exceeds its lanes)");
+    switch (p->fev_cw * 100 + p->fev_warps) {
+    case 404: return fev_launch_mode<4, 4>(a, mode, count, st);
+    case 408: return fev_launch_mode<4, 8>(a, mode, count, st);
+    case 804: return fev_launch_mode<8, 4>(a, mode, count, st);
+    case 808: return fev_launch_mode<8, 8>(a, mode, count, st);
+    case 1604: return fev_launch_mode<16, 4>(a, mode, count, st);
+    default: break;
+    }
+    return pax_set_error(PAX_ERR_INVALID, "pax_ax: unsupported fan configuration CW=%d warps=%d", p->fev_cw,
+                         p->fev_warps);
+}
+
+// Epoch length, rows per warp and launch shape from the plan's geometry.
+int pax_fan_ev_configure(PaxPlan *p)
+{
+    const PaxGeo &g = p->geo;
+    const double dmax = std::fmax(g.dVoxelX, g.dVoxelY);
+    // largest |dz| per step of any ray, in slices
+    double slope = 0.0;
+    for (const AngleDev &A : p->h_angles) {
+        const double nmin = std::ceil((double)A.DSD / dmax / g.accuracy);
+        const double za = std::fabs(A.oz - A.sz), zb = std::fabs(A.oz + (g.nDetecV - 1) * A.vz - A.sz);
+        slope = std::fmax(slope, std::fmax(za, zb) / nmin);
+    }
+    const char *e;
+    int cw = 4, nw = 8;
+    if ((e = getenv("PAX_FAN_CW")) && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16)) cw = atoi(e);   // tuning hooks
+    if ((e = getenv("PAX_FAN_NW")) && (atoi(e) == 4 || atoi(e) == 8)) nw = atoi(e);
+    if (cw == 16) nw = 4;
+    // a single row must fit the 32 lanes (128 slices) of a pass over one epoch, with room to spare for its
+    // neighbours: halve the epoch until its z travel is at most 64 slices
+    int ep = 128;
+    if ((e = getenv("PAX_FAN_EPOCH")) && atoi(e) >= cw) ep = atoi(e) / cw * cw;
+    while (ep >= cw && ep * slope > 64.0) ep /= 2;
+    if (ep < cw) ep = 0;
+    else ep = ep / cw * cw;
+    p->fev_epoch = ep;
+    p->fev_cw = cw;
+    p->fev_warps = nw;
+    const int tiles = (g.nDetecV + FAN_MAXROWS - 1) / FAN_MAXROWS;
+    p->fev_rows = (g.nDetecV + tiles - 1) / tiles;
+    return PAX_OK;
+}

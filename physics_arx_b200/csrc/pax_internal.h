@@ -44,6 +44,12 @@ struct PaxPlan {
     int fan_warps;              // warps per CTA
     double fan_run;             // mean length (rows) of the equal-n runs of a detector column
     int *d_fault;               // device word the fan kernel raises if a z window overflowed
+    // ax_fan_ev.cu (event-driven fan-plane kernel)
+    int fan_impl;               // 1: ax_fan_ev.cu (default), 0: ax_fan.cu (PAX_FAN_IMPL=old)
+    int fev_rows;               // detector rows one warp walks
+    int fev_epoch;              // steps per epoch (0: the kernel does not fit the geometry)
+    int fev_cw;                 // steps per window (ring depth)
+    int fev_warps;              // warps per CTA
 };
 
 
@@ -72,6 +78,7 @@ struct AxArgs {
     float whx, why, whz, wthr;
     int fan_rows;                 // ax_fan.cu: detector rows one warp walks
     int fan_piece;                // ax_fan.cu: most rows that share one z window
+    int fan_epoch;                // ax_fan_ev.cu: steps per epoch
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
     int *fault;                   // ax_fan.cu: set to 1 if a z window did not fit (never, by construction)
 };
@@ -79,6 +86,9 @@ struct AxArgs {
 // ax_fan.cu
 int pax_fan_configure(PaxPlan *p);
 int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a, int mode, int count, cudaStream_t st);
+// ax_fan_ev.cu
+int pax_fan_ev_configure(PaxPlan *p);
+int pax_ax_fan_ev_launch(const PaxPlan *p, const AxArgs &a, int mode, int count, cudaStream_t st);
 
 int pax_set_error(int code, const char *fmt, ...);
 

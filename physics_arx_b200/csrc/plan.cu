@@ -1,6 +1,7 @@
 // Plan (per-geometry device constants), error reporting, layout conversion, and the
 // small elementwise / reduction kernels of the path.  sm_100a only.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -98,6 +99,11 @@ extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, Pax
     cudaMemset(p->d_fault, 0, sizeof(int));
     p->projector = PAX_PROJECTOR_AUTO;
     pax_fan_configure(p);
+    pax_fan_ev_configure(p);
+    {
+        const char *impl = getenv("PAX_FAN_IMPL");             // tuning hook: "old" = ax_fan.cu
+        p->fan_impl = (impl && strcmp(impl, "old") == 0) ? 0 : 1;
+    }
     *out = p;
     return PAX_OK;
 }
