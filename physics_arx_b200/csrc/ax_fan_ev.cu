@@ -38,19 +38,23 @@
 #include "pax_internal.h"
 
 #define FAN_MAXSEG 8            // runs (pieces of runs) packed into the lanes of one pass
-#define FAN_QCAP 128            // crossing events served per round
+#define FAN_QCAP 96             // crossing events served per round
 #define FAN_MAXROWS 1024        // detector rows one warp walks
+#define FAN_EPMAX 128           // most steps per epoch
 
 template <int CW>
 struct __align__(16) FanEvSmem {
-    float4 ring[CW * 64];                      // [step][half][lane]: (A0,A1,C0,C1) / (A2,A3,C2,C3) of the lane's quad
-    float4 w[FAN_MAXSEG][2 * CW + 1];          // per run and step (two windows): three bilinear weights + cell offset
-    float rtab[CW + 4];                        // rcp(step) of the window's steps (the crossing predicate)
+    float ring[CW * 256 + 8];                  // 4 guard floats, then [step][A of the 128 lane slices | C of them]
+    float4 w[FAN_MAXSEG][CW + 1];              // per lattice (distinct n): three bilinear weights + cell offset of the
+                                               // steps w0+1 .. w0+CW of the window (slot CW: the epoch's first step)
+    float4 c_geo[FAN_MAXSEG];                  // per lattice: {ddx, ddy, fraction x, fraction y} of the epoch's origin
+    int4 c_cell[FAN_MAXSEG];                   // per lattice: {origin cell x, y, first step, last step} of the epoch
+    float4 s_f[FAN_MAXSEG];                    // per run: {n / vz, dz per step of row 0, its increment per row, z_ref of row 0}
+    int4 s_i[FAN_MAXSEG];                      // per run: {first lane, lanes, first quad, last step of the epoch}
+    float s_zrefv[FAN_MAXSEG];                 // per run: increment of z_ref per row
+    int s_ra[FAN_MAXSEG], s_rb[FAN_MAXSEG], s_cls[FAN_MAXSEG], c_n[FAN_MAXSEG];
+    float rtab[FAN_EPMAX + 4];                 // rcp(step) of the epoch's steps (the crossing predicate)
     unsigned queue[FAN_QCAP];
-    int s_ra[FAN_MAXSEG], s_rb[FAN_MAXSEG], s_base[FAN_MAXSEG], s_qa[FAN_MAXSEG], s_nq[FAN_MAXSEG];
-    int s_i0[FAN_MAXSEG], s_i1[FAN_MAXSEG], s_exc[FAN_MAXSEG], s_eyc[FAN_MAXSEG];
-    float s_nvz[FAN_MAXSEG], s_s0[FAN_MAXSEG], s_zvr[FAN_MAXSEG], s_zref0[FAN_MAXSEG], s_zrefv[FAN_MAXSEG];
-    float s_exf[FAN_MAXSEG], s_eyf[FAN_MAXSEG], s_fddx[FAN_MAXSEG], s_fddy[FAN_MAXSEG];
     unsigned char lane_seg[32];
     unsigned starts[FAN_MAXROWS / 32];         // bit r of word w: row 32w+r starts a run of equal n
 };
@@ -89,6 +93,13 @@ __device__ __forceinline__ void fev_ld4_if(float4 &v, const void *p, bool take)
                  : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
                  : "r"((int)take), "l"(p));
 }
+// base + (unsigned) byte offset in one instruction (IMAD.WIDE.U32)
+__device__ __forceinline__ const char *fev_at(const char *base, unsigned off)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"((unsigned long long)base));
+    return reinterpret_cast<const char *>(r);
+}
 __device__ __forceinline__ float2 fev_mul2(float w, float a, float b)
 {
     return __fmul2_rn(make_float2(w, w), make_float2(a, b));
@@ -102,8 +113,7 @@ __device__ __forceinline__ float2 fev_fma2(float w, float a, float b, float2 acc
 // (a = (k - sz) n / vz, b = dz0 / vz).  Every use goes through this function, bit for bit.
 __device__ __forceinline__ int fev_cv(float a, float r, float b)
 {
-    const float x = fminf(fmaxf(__fmaf_rn(a, r, -b), -1.0e6f), 1.0e6f);
-    return (int)ceilf(x);
+    return __float2int_ru(__fmaf_rn(a, r, -b));            // F2I saturates: monotone for any finite input
 }
 __device__ __forceinline__ float fev_ak(int k, float szf, float nvz)
 {
@@ -114,8 +124,8 @@ __device__ __forceinline__ float fev_rcp_step(int i)
     return i > 0 ? __frcp_rn((float)i) : 2.0f;             // decreasing in i, finite at the source
 }
 
-template <int CW, int NWARPS, int MODE>
-__global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
+template <int CW, int NWARPS, int MINB, int MODE>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
 {
     extern __shared__ __align__(16) unsigned char fev_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,20 +188,21 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
             const int e1 = min(e0 + EP - 1, Emax);
             const int ref = e0 + (EP >> 1);
             const int nwin = (e1 - e0 + CW) / CW;
+            for (int t = lane; t <= EP; t += 32) sm.rtab[t] = fev_rcp_step(e0 + t);
             int cur = 0;
 #pragma unroll 1
             while (cur < nRows) {
                 // ================= pack runs (or pieces of runs) into the lanes of one pass (uniform over the warp)
-                int nseg = 0, used = 0, rowA = -1, rowB = -1;
+                int nseg = 0, ncls = 0, used = 0;
 #pragma unroll 1
                 while (cur < nRows && nseg < FAN_MAXSEG && used < 31) {
                     const int e = fev_next_start(sm.starts, cur, nRows);
                     const double dzc = dz0 + (double)cur * vz;
                     const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
-                    const double rn = 1.0 / (double)nrun;
                     const int I0 = max((int)ceil(lam0 * (double)nrun), 0), I1 = (int)floor(lam1 * (double)nrun);
                     const int ja = max(I0, e0), jb = min(I1, e1);
                     if (ja > jb) { cur = e; continue; }           // the run has no sample in this epoch
+                    const double rn = 1.0 / (double)nrun;
                     const float s0f = (float)(dz0 * rn), zvrf = (float)(vz * rn);
                     const float fa = (float)ja, fb = (float)jb;
                     const float sA = fmaf((float)cur, zvrf, s0f);
@@ -203,8 +214,9 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
                     const float lim = (float)(4 * (qa + avail) - 1) - 8e-3f - szf;
                     float rmaxf = (float)(e - 1);
                     if (zvrf > 0.f) {
-                        if (fb > 0.f) rmaxf = fminf(rmaxf, (lim / fb - s0f) / zvrf - 1e-2f);
-                        if (fa > 0.f) rmaxf = fminf(rmaxf, (lim / fa - s0f) / zvrf - 1e-2f);
+                        const float rz = __frcp_rn(zvrf);
+                        if (fb > 0.f) rmaxf = fminf(rmaxf, (__fdividef(lim, fb) - s0f) * rz - 2e-2f);
+                        if (fa > 0.f) rmaxf = fminf(rmaxf, (__fdividef(lim, fa) - s0f) * rz - 2e-2f);
                     }
                     int rb = min(max((int)floorf(fmaxf(rmaxf, -1.0f)) + 1, cur + 1), e);
                     int nq;
@@ -218,132 +230,138 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
                     }
                     if (nq > avail) {
                         if (used > 0) break;                      // start a new pass with this run
-                        if (lane == 0 && a.fault) atomicExch(a.fault, 1);   // a single row does not fit: see pax_fan_configure
+                        if (lane == 0 && a.fault) atomicExch(a.fault, 1);   // a single row does not fit: see pax_fan_ev_configure
                         nq = avail;
                     }
+                    // the run's lattice: runs with the same n (below and above the source plane) share their steps
+                    int cls = 0;
+                    while (cls < ncls && sm.c_n[cls] != nrun) ++cls;
                     if (lane == 0) {
                         const int g = nseg;
-                        sm.s_ra[g] = cur; sm.s_rb[g] = rb; sm.s_base[g] = used; sm.s_qa[g] = qa; sm.s_nq[g] = nq;
-                        sm.s_i0[g] = ja; sm.s_i1[g] = jb;
-                        sm.s_nvz[g] = (float)((double)nrun / vz);
-                        sm.s_s0[g] = s0f; sm.s_zvr[g] = zvrf;
-                        sm.s_zref0[g] = (float)(sz + (double)ref * dz0 * rn);
+                        sm.s_ra[g] = cur; sm.s_rb[g] = rb; sm.s_cls[g] = cls;
+                        sm.s_i[g] = make_int4(used, nq, qa, jb);
+                        sm.s_f[g] = make_float4((float)((double)nrun / vz), s0f, zvrf, (float)(sz + (double)ref * dz0 * rn));
                         sm.s_zrefv[g] = (float)((double)ref * vz * rn);
-                        // in-plane origin of the epoch, split in double into an integer cell and a fraction; steps
-                        // add t*d to the fraction in fp32 (t < EP): a position is good to a few 1e-6 voxels
-                        const double ddx = dx * rn, ddy = dy * rn;
-                        const double ex = sx + (double)e0 * ddx, ey = sy + (double)e0 * ddy;
-                        const double exi = floor(ex), eyi = floor(ey);
-                        sm.s_exc[g] = (int)exi; sm.s_eyc[g] = (int)eyi;
-                        sm.s_exf[g] = (float)(ex - exi); sm.s_eyf[g] = (float)(ey - eyi);
-                        sm.s_fddx[g] = (float)ddx; sm.s_fddy[g] = (float)ddy;
+                        if (cls == ncls) {
+                            // in-plane origin of the epoch, split in double into an integer cell and a fraction; steps
+                            // add t*d to the fraction in fp32 (t < EP): a position is good to a few 1e-6 voxels
+                            const double ddx = dx * rn, ddy = dy * rn;
+                            const double ex = sx + (double)e0 * ddx, ey = sy + (double)e0 * ddy;
+                            const double exi = floor(ex), eyi = floor(ey);
+                            sm.c_n[cls] = nrun;
+                            sm.c_geo[cls] = make_float4((float)ddx, (float)ddy, (float)(ex - exi), (float)(ey - eyi));
+                            sm.c_cell[cls] = make_int4((int)exi, (int)eyi, ja, jb);
+                        }
                     }
-                    if (rowA < 0) rowA = cur;
-                    rowB = rb;
+                    __syncwarp();
+                    if (cls == ncls) ++ncls;
                     used += nq;
                     ++nseg;
                     cur = rb;
                 }
                 if (nseg == 0) continue;
-                __syncwarp();
 
                 // ================= the pass
                 int myseg = -1;
 #pragma unroll 1
-                for (int g = 0; g < nseg; ++g)
-                    if (lane >= sm.s_base[g] && lane < sm.s_base[g] + sm.s_nq[g]) myseg = g;
+                for (int g = 0; g < nseg; ++g) {
+                    const int4 si = sm.s_i[g];
+                    if (lane >= si.x && lane < si.x + si.y) myseg = g;
+                }
                 const bool on = myseg >= 0;
                 const int sg = on ? myseg : 0;
-                const int quad = sm.s_qa[sg] + lane - sm.s_base[sg];
+                const int4 mysi = sm.s_i[sg];
+                const int quad = mysi.z + lane - mysi.x;
                 const int segra = sm.s_ra[sg], segrb = sm.s_rb[sg];
-                const int segjb = sm.s_i1[sg];                    // last step of my run in this epoch: no sample, hence
+                const int segjb = mysi.w;                         // last step of my run in this epoch: no sample, hence
                                                                   // no crossing to serve, after it
-                sm.lane_seg[lane] = (unsigned char)(on ? myseg : 255);
+                sm.lane_seg[lane] = (unsigned char)sg;
                 float ak0, ak1, ak2, ak3;
                 {
-                    const float nvz = sm.s_nvz[sg];
+                    const float nvz = sm.s_f[sg].x;
                     ak0 = fev_ak(4 * quad + 0, szf, nvz); ak1 = fev_ak(4 * quad + 1, szf, nvz);
                     ak2 = fev_ak(4 * quad + 2, szf, nvz); ak3 = fev_ak(4 * quad + 3, szf, nvz);
                 }
                 int cs0, cs1, cs2, cs3;                           // rows above my boundaries so far: [cs, segrb)
                 {
-                    const float r0 = fev_rcp_step(e0);
+                    const float r0 = sm.rtab[0];
                     cs0 = min(max(fev_cv(ak0, r0, bq), segra), segrb); cs1 = min(max(fev_cv(ak1, r0, bq), segra), segrb);
                     cs2 = min(max(fev_cv(ak2, r0, bq), segra), segrb); cs3 = min(max(fev_cv(ak3, r0, bq), segra), segrb);
                 }
-                const char *bb = reinterpret_cast<const char *>(a.vol0 + 4 * (on ? quad : 0));
-                const float4 *wp = sm.w[sg];
-                float2 A01 = make_float2(0.f, 0.f), A23 = A01, C01 = A01, C23 = A01;
+                // the four corner columns of in-plane cell (0,0), at my quad
+                const char *b00 = reinterpret_cast<const char *>(a.vol0 + 4 * (on ? quad : 0));
+                const char *b01 = b00 + dx4, *b10 = b00 + dy4, *b11 = b10 + dx4;
+                const float4 *wp = sm.w[sm.s_cls[sg]];
+                float *const ring = sm.ring + 4;
+                float4 Aq = make_float4(0.f, 0.f, 0.f, 0.f), Cq = Aq;     // running (A, C) of my four slices
                 float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
+                // event words of my four slices: row | slot << 16 | edge flags (no neighbour slice below / above
+                // inside the run's lanes: it is a zero slice) | direction
+                const unsigned evw = ((unsigned)(lane * 4) << 16);
+                const unsigned elo = (lane == mysi.x) ? (1u << 23) : 0u, ehi = (lane == mysi.x + mysi.y - 1) ? (1u << 24) : 0u;
 
-                // weights and cells of window m of the epoch (steps e0 + m CW ...), all runs of the pass
-                auto fill_w = [&](int m) {
-                    const int w0 = e0 + m * CW, half = (m & 1) * CW;
-                    for (int q = lane; q < nseg * CW; q += 32) {
-                        const int g = q / CW, t = q - g * CW, i = w0 + t;
+                // weights and cells of `count` steps from `first` on into slots slot0.., all lattices of the pass
+                auto fill_w = [&](int first, int count, int slot0) {
+                    for (int q = lane; q < ncls * count; q += 32) {
+                        const int g = q / count, t = q - g * count, i = first + t;
+                        const int4 cc = sm.c_cell[g];
                         // a step outside the run's range reads the all-zero rim column (0,0) with weight one
                         float4 w = make_float4(1.f, 0.f, 0.f, __uint_as_float(0u));
-                        if (i >= sm.s_i0[g] && i <= sm.s_i1[g]) {
-                            const int exc = sm.s_exc[g], eyc = sm.s_eyc[g];
+                        if (i >= cc.z && i <= cc.w) {
+                            const float4 cg = sm.c_geo[g];
                             const float tf = (float)(i - e0);
-                            const float px = fmaf(tf, sm.s_fddx[g], sm.s_exf[g]), py = fmaf(tf, sm.s_fddy[g], sm.s_eyf[g]);
-                            const float flx = floorf(px), fly = floorf(py);
-                            const int cx = min(max(exc + (int)flx, 0), xmaxc);
-                            const int cy = min(max(eyc + (int)fly, 0), ymaxc);
+                            const float px = fmaf(tf, cg.x, cg.z), py = fmaf(tf, cg.y, cg.w);
+                            const int ix = __float2int_rd(px), iy = __float2int_rd(py);
+                            const int cx = min(max(cc.x + ix, 0), xmaxc);
+                            const int cy = min(max(cc.y + iy, 0), ymaxc);
                             // fraction against the CLAMPED cell: a sample the double clip admitted may sit an ulp
                             // outside in fp32, and must then weigh the rim, not the next column
-                            const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
-                            const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
+                            const float fx = fminf(fmaxf(px - (float)(cx - cc.x), 0.f), 1.f);
+                            const float fy = fminf(fmaxf(py - (float)(cy - cc.y), 0.f), 1.f);
                             const unsigned off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
                             const float gx = 1.f - fx, gy = 1.f - fy;
                             w = make_float4(gx * gy, fx * gy, gx * fy, __uint_as_float(off));
                         }
-                        sm.w[g][half + t] = w;
+                        sm.w[g][slot0 + t] = w;
                     }
                 };
-                fill_w(0);
+                fill_w(e0, 1, CW);
+                fill_w(e0 + 1, CW, 0);
                 __syncwarp();
-                float4 wv = wp[0];
+                float4 wv = wp[CW];
                 unsigned off = __float_as_uint(wv.w);
-                {
-                    const char *p00 = bb + off, *p10 = p00 + dy4;
-                    fev_ld4_if(c00, p00, on); fev_ld4_if(c01, p00 + dx4, on);
-                    fev_ld4_if(c10, p10, on); fev_ld4_if(c11, p10 + dx4, on);
-                }
+                fev_ld4_if(c00, fev_at(b00, off), on); fev_ld4_if(c01, fev_at(b01, off), on);
+                fev_ld4_if(c10, fev_at(b10, off), on); fev_ld4_if(c11, fev_at(b11, off), on);
                 float jf = (float)(e0 - ref);
 #pragma unroll 1
                 for (int m = 0; m < nwin; ++m) {
                     const int w0 = e0 + m * CW;
-                    fill_w(m + 1);                                // the next window (its first step is prefetched below)
-                    if (lane <= CW) sm.rtab[lane] = fev_rcp_step(w0 + lane);
-                    __syncwarp();
+                    const float *rt = sm.rtab + m * CW;            // rt[t] = rcp(w0 + t)
+                    if (m) { fill_w(w0 + 1, CW, 0); __syncwarp(); }
                     // ---- CW steps: running (A, C) of my four slices into the ring
-                    {
-                        const int half = (m & 1) * CW;
 #pragma unroll
-                        for (int t = 0; t < CW; ++t) {
-                            const int tn = (t + 1 < CW) ? half + t + 1 : (half ^ CW);
-                            const float4 wn = wp[tn];
-                            const unsigned offn = __float_as_uint(wn.w);
-                            const bool chg = on && offn != off;
-                            const float w11 = 1.f - wv.x - wv.y - wv.z;          // the weights sum to one
-                            const char *p00 = bb + offn, *p10 = p00 + dy4;
-                            float2 v0 = fev_mul2(wv.x, c00.x, c00.y), v1 = fev_mul2(wv.x, c00.z, c00.w);
-                            v0 = fev_fma2(wv.y, c01.x, c01.y, v0); v1 = fev_fma2(wv.y, c01.z, c01.w, v1);
-                            v0 = fev_fma2(wv.z, c10.x, c10.y, v0); v1 = fev_fma2(wv.z, c10.z, c10.w, v1);
-                            v0 = fev_fma2(w11, c11.x, c11.y, v0); v1 = fev_fma2(w11, c11.z, c11.w, v1);
-                            // the columns of the next step, as soon as this one has consumed the registers
-                            fev_ld4_if(c00, p00, chg); fev_ld4_if(c01, p00 + dx4, chg);
-                            fev_ld4_if(c10, p10, chg); fev_ld4_if(c11, p10 + dx4, chg);
-                            A01 = __fadd2_rn(A01, v0); A23 = __fadd2_rn(A23, v1);
-                            C01 = __ffma2_rn(make_float2(jf, jf), v0, C01);
-                            C23 = __ffma2_rn(make_float2(jf, jf), v1, C23);
-                            jf += 1.f;
-                            sm.ring[t * 64 + lane] = make_float4(A01.x, A01.y, C01.x, C01.y);
-                            sm.ring[t * 64 + 32 + lane] = make_float4(A23.x, A23.y, C23.x, C23.y);
-                            off = offn;
-                            wv = wn;
-                        }
+                    for (int t = 0; t < CW; ++t) {
+                        const float4 wn = wp[t];                   // the next step
+                        const unsigned offn = __float_as_uint(wn.w);
+                        const bool chg = on && offn != off;
+                        const float w11 = 1.f - wv.x - wv.y - wv.z;              // the weights sum to one
+                        float2 v0 = fev_mul2(wv.x, c00.x, c00.y), v1 = fev_mul2(wv.x, c00.z, c00.w);
+                        v0 = fev_fma2(wv.y, c01.x, c01.y, v0); v1 = fev_fma2(wv.y, c01.z, c01.w, v1);
+                        v0 = fev_fma2(wv.z, c10.x, c10.y, v0); v1 = fev_fma2(wv.z, c10.z, c10.w, v1);
+                        v0 = fev_fma2(w11, c11.x, c11.y, v0); v1 = fev_fma2(w11, c11.z, c11.w, v1);
+                        // the columns of the next step, as soon as this one has consumed the registers
+                        fev_ld4_if(c00, fev_at(b00, offn), chg); fev_ld4_if(c01, fev_at(b01, offn), chg);
+                        fev_ld4_if(c10, fev_at(b10, offn), chg); fev_ld4_if(c11, fev_at(b11, offn), chg);
+                        // (scalar accumulates: packed ones would pin the sums to register pairs that the 16-byte
+                        // stores then have to gather with eight moves)
+                        Aq.x += v0.x; Aq.y += v0.y; Aq.z += v1.x; Aq.w += v1.y;
+                        Cq.x = fmaf(jf, v0.x, Cq.x); Cq.y = fmaf(jf, v0.y, Cq.y);
+                        Cq.z = fmaf(jf, v1.x, Cq.z); Cq.w = fmaf(jf, v1.y, Cq.w);
+                        jf += 1.f;
+                        *reinterpret_cast<float4 *>(ring + t * 256 + 4 * lane) = Aq;
+                        *reinterpret_cast<float4 *>(ring + t * 256 + 128 + 4 * lane) = Cq;
+                        off = offn;
+                        wv = wn;
                     }
                     __syncwarp();
                     // ---- crossings at steps w0+1 .. iend (prefix through the step before, i.e. ring row t-1)
@@ -353,15 +371,15 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
                     {
                         const int il = min(iend, segjb);
                         int c0 = cs0, c1 = cs1, c2 = cs2, c3 = cs3;
-                        if (il > w0) {
-                            const float re = sm.rtab[il - w0];
+                        if (on && il > w0) {
+                            const float re = rt[il - w0];
                             c0 = min(max(fev_cv(ak0, re, bq), segra), segrb); c1 = min(max(fev_cv(ak1, re, bq), segra), segrb);
                             c2 = min(max(fev_cv(ak2, re, bq), segra), segrb); c3 = min(max(fev_cv(ak3, re, bq), segra), segrb);
                         }
-                        lo0 = min(c0, cs0); n0 = on ? abs(c0 - cs0) : 0; up |= (c0 < cs0) ? 1u : 0u;
-                        lo1 = min(c1, cs1); n1 = on ? abs(c1 - cs1) : 0; up |= (c1 < cs1) ? 2u : 0u;
-                        lo2 = min(c2, cs2); n2 = on ? abs(c2 - cs2) : 0; up |= (c2 < cs2) ? 4u : 0u;
-                        lo3 = min(c3, cs3); n3 = on ? abs(c3 - cs3) : 0; up |= (c3 < cs3) ? 8u : 0u;
+                        lo0 = min(c0, cs0); n0 = abs(c0 - cs0); up |= (c0 < cs0) ? 0x80000000u : 0u;
+                        lo1 = min(c1, cs1); n1 = abs(c1 - cs1); up |= (c1 < cs1) ? 0x40000000u : 0u;
+                        lo2 = min(c2, cs2); n2 = abs(c2 - cs2); up |= (c2 < cs2) ? 0x20000000u : 0u;
+                        lo3 = min(c3, cs3); n3 = abs(c3 - cs3); up |= (c3 < cs3) ? 0x10000000u : 0u;
                         cs0 = c0; cs1 = c1; cs2 = c2; cs3 = c3;
                     }
                     const int mine = n0 + n1 + n2 + n3;
@@ -374,85 +392,73 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll 1
                     for (int qb = 0; qb < total; qb += FAN_QCAP) {
-                        // my events into the queue: (row, slot = 4*lane + slice, direction)
+                        // my events into the queue
                         {
-                            int idx = incl - mine - qb;
-                            const unsigned slot = (unsigned)(lane * 4) << 16;
-                            for (int r = 0; r < n0; ++r, ++idx)
-                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo0 + r) | slot | ((up & 1u) << 31);
-                            for (int r = 0; r < n1; ++r, ++idx)
-                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo1 + r) | (slot + (1u << 16)) | ((up & 2u) << 30);
-                            for (int r = 0; r < n2; ++r, ++idx)
-                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo2 + r) | (slot + (2u << 16)) | ((up & 4u) << 29);
-                            for (int r = 0; r < n3; ++r, ++idx)
-                                if ((unsigned)idx < FAN_QCAP) sm.queue[idx] = (unsigned)(lo3 + r) | (slot + (3u << 16)) | ((up & 8u) << 28);
+                            const int i0 = incl - mine - qb, i1 = i0 + n0, i2 = i1 + n1, i3 = i2 + n2;
+                            const unsigned e0w = (unsigned)lo0 | evw | elo | (up & 0x80000000u);
+                            const unsigned e1w = (unsigned)lo1 | (evw + (1u << 16)) | ((up << 1) & 0x80000000u);
+                            const unsigned e2w = (unsigned)lo2 | (evw + (2u << 16)) | ((up << 2) & 0x80000000u);
+                            const unsigned e3w = (unsigned)lo3 | (evw + (3u << 16)) | ehi | ((up << 3) & 0x80000000u);
+                            const int nmax = max(max(n0, n1), max(n2, n3));
+                            for (int r = 0; r < nmax; ++r) {
+                                if (r < n0 && (unsigned)(i0 + r) < FAN_QCAP) sm.queue[i0 + r] = e0w + r;
+                                if (r < n1 && (unsigned)(i1 + r) < FAN_QCAP) sm.queue[i1 + r] = e1w + r;
+                                if (r < n2 && (unsigned)(i2 + r) < FAN_QCAP) sm.queue[i2 + r] = e2w + r;
+                                if (r < n3 && (unsigned)(i3 + r) < FAN_QCAP) sm.queue[i3 + r] = e3w + r;
+                            }
                         }
                         __syncwarp();
                         const int nev = min(FAN_QCAP, total - qb);
                         for (int q = lane; q < nev; q += 32) {
                             const unsigned ev = sm.queue[q];
                             const int v = (int)(ev & 0xffffu), slot = (int)((ev >> 16) & 0x7fu);
-                            const bool isup = (ev >> 31) != 0;
-                            const int L = slot >> 2, s = slot & 3;
-                            const int g = sm.lane_seg[L];
-                            const int base = sm.s_base[g], nq = sm.s_nq[g];
-                            const int k = 4 * (sm.s_qa[g] + L - base) + s;
-                            const float ak = fev_ak(k, szf, sm.s_nvz[g]);
-                            // first step of the window at which the row is on the new side (binary search on
-                            // the monotone predicate; at iend it is, at w0 it is not)
-                            int tl = 1, th = min(iend, sm.s_i1[g]) - w0;
-                            while (tl < th) {
-                                const int mid = (tl + th) >> 1;
-                                const bool above = v >= fev_cv(ak, sm.rtab[mid], bq);
-                                if (above == isup) th = mid; else tl = mid + 1;
-                            }
-                            const float4 *row = sm.ring + (tl - 1) * 64;
-                            const int pa = 2 * L + (s >> 1);              // my slice pair, and the one holding the
-                            const int pb = (s & 1) ? pa + 1 : pa - 1;     // neighbour on the other side
-                            const float4 P = row[(pa & 1) * 32 + (pa >> 1)];
-                            float4 Q = make_float4(0.f, 0.f, 0.f, 0.f);   // beyond the run's lanes: zero slices
-                            if (pb >= 2 * base && pb < 2 * (base + nq)) Q = row[(pb & 1) * 32 + (pb >> 1)];
-                            float d2a, d2c;
-                            if (s & 1) { d2a = P.x - 2.f * P.y + Q.x; d2c = P.z - 2.f * P.w + Q.z; }
-                            else       { d2a = Q.y - 2.f * P.x + P.y; d2c = Q.w - 2.f * P.z + P.w; }
-                            const float fv = (float)v;
-                            const float sv = fmaf(fv, sm.s_zvr[g], sm.s_s0[g]);
-                            const float tau = fmaf(fv, sm.s_zrefv[g], sm.s_zref0[g]) - (float)k;
+                            const int g = sm.lane_seg[slot >> 2];
+                            const int4 si = sm.s_i[g];
+                            const float4 sf = sm.s_f[g];
+                            const float fk = (float)(4 * (si.z - si.x) + slot), fv = (float)v;
+                            const float ak = __fmul_rn(__fsub_rn(fk, szf), sf.x);
+                            // first step of the window at which the row is on the new side of the boundary.  The
+                            // closed form may differ from the predicate's by a step when z hits the boundary to
+                            // ~1e-5: harmless, the interpolant is continuous there (only WHICH window serves the
+                            // crossing has to agree with the pair found at the epoch's end, and that is the predicate's)
+                            const int th = min(iend, si.w) - w0;
+                            const int tl = min(max(__float2int_ru(__fdividef(ak, fv + bq)) - w0, 1), th);
+                            const float *row = ring + (tl - 1) * 256 + slot;
+                            float am = row[-1], a0_ = row[0], ap = row[1], cm = row[127], c0_ = row[128], cp = row[129];
+                            if (ev & (1u << 23)) { am = 0.f; cm = 0.f; }
+                            if (ev & (1u << 24)) { ap = 0.f; cp = 0.f; }
+                            const float d2a = fmaf(-2.f, a0_, am + ap), d2c = fmaf(-2.f, c0_, cm + cp);
+                            const float sv = fmaf(fv, sf.z, sf.y);
+                            const float tau = fmaf(fv, sm.s_zrefv[g], sf.w) - fk;
                             const float val = fmaf(tau, d2a, sv * d2c);
-                            atomicAdd(rsum + v, isup ? -val : val);
+                            atomicAdd(rsum + v, (int)ev < 0 ? -val : val);
                         }
                         __syncwarp();
                     }
                 }
-                // ---- end of the epoch: every row reads its slice pair once (prefix through step e1)
+                // ---- end of the epoch: every row reads its slice pair once
                 {
-                    const float4 *row = sm.ring + (e1 - (e0 + (nwin - 1) * CW)) * 64;
+                    const float *row = ring + (e1 - (e0 + (nwin - 1) * CW)) * 256;
 #pragma unroll 1
                     for (int g = 0; g < nseg; ++g) {
+                        const int4 si = sm.s_i[g];
+                        const float4 sf = sm.s_f[g];
+                        const float zrv = sm.s_zrefv[g];
                         // the run's last step of the epoch; the sums do not change after it (G = 0)
-                        const float re = fev_rcp_step(sm.s_i1[g]), fe = (float)sm.s_i1[g];
-                        const int base = sm.s_base[g], nq = sm.s_nq[g], k0 = 4 * sm.s_qa[g];
-                        const float nvz = sm.s_nvz[g], s0f = sm.s_s0[g], zvrf = sm.s_zvr[g];
-                        const float zr0 = sm.s_zref0[g], zrv = sm.s_zrefv[g];
+                        const float re = sm.rtab[si.w - e0], fe = (float)si.w;
+                        const int k0 = 4 * si.z;
                         for (int v = sm.s_ra[g] + lane; v < sm.s_rb[g]; v += 32) {
                             const float fv = (float)v;
-                            const float sv = fmaf(fv, zvrf, s0f);
-                            int K = (int)floorf(fminf(fmaxf(fmaf(fe, sv, szf), -1.0e6f), 1.0e6f));
+                            const float sv = fmaf(fv, sf.z, sf.y);
+                            int K = __float2int_rd(fmaf(fe, sv, szf));
                             // the pair the PREDICATE puts the row in (an ulp of z may disagree with it)
-                            if (v >= fev_cv(fev_ak(K + 1, szf, nvz), re, bq)) ++K;
-                            else if (v < fev_cv(fev_ak(K, szf, nvz), re, bq)) --K;
+                            if (v >= fev_cv(fev_ak(K + 1, szf, sf.x), re, bq)) ++K;
+                            else if (v < fev_cv(fev_ak(K, szf, sf.x), re, bq)) --K;
                             const int kap = K - k0;
-                            if (kap >= 0 && kap + 1 < 4 * nq) {
-                                const int pa = 2 * base + (kap >> 1);
-                                const float4 P = row[(pa & 1) * 32 + (pa >> 1)];
-                                float aK, aK1, cK, cK1;
-                                if (kap & 1) {
-                                    const float4 Q = row[((pa + 1) & 1) * 32 + ((pa + 1) >> 1)];
-                                    aK = P.y; cK = P.w; aK1 = Q.x; cK1 = Q.z;
-                                } else {
-                                    aK = P.x; aK1 = P.y; cK = P.z; cK1 = P.w;
-                                }
-                                const float tau = fmaf(fv, zrv, zr0) - (float)K;
+                            if (kap >= 0 && kap + 1 < 4 * si.y) {
+                                const float *pr = row + 4 * si.x + kap;
+                                const float aK = pr[0], aK1 = pr[1], cK = pr[128], cK1 = pr[129];
+                                const float tau = fmaf(fv, zrv, sf.w) - (float)K;
                                 rsum[v] += fmaf(sv, cK1 - cK, fmaf(tau, aK1 - aK, aK));
                             }
                         }
@@ -527,24 +533,24 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan_ev(const AxArgs a)
 }
 
 // ------------------------------------------------------------------------------ host side
-template <int CW, int NWARPS, int MODE>
+template <int CW, int NWARPS, int MINB, int MODE>
 static int fev_launch(const AxArgs &a, int count, cudaStream_t st)
 {
     const size_t per_warp = sizeof(FanEvSmem<CW>) + (size_t)((a.fan_rows + 3) & ~3) * sizeof(float);
     const size_t smem = per_warp * NWARPS;
     PAX_REQUIRE(smem <= 227 * 1024, "pax_ax: fan-plane tables do not fit shared memory");
-    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan_ev<CW, NWARPS, MODE>,
+    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan_ev<CW, NWARPS, MINB, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(pax_cdiv(a.nu, NWARPS), count, pax_cdiv(a.nv, a.fan_rows));
-    k_ax_fan_ev<CW, NWARPS, MODE><<<grid, NWARPS * 32, smem, st>>>(a);
+    k_ax_fan_ev<CW, NWARPS, MINB, MODE><<<grid, NWARPS * 32, smem, st>>>(a);
     return PAX_OK;
 }
 
-template <int CW, int NWARPS>
+template <int CW, int NWARPS, int MINB>
 static int fev_launch_mode(const AxArgs &a, int mode, int count, cudaStream_t st)
 {
-    return mode == PAX_AX_PLAIN ? fev_launch<CW, NWARPS, PAX_AX_PLAIN>(a, count, st)
-                                : fev_launch<CW, NWARPS, PAX_AX_RESIDUAL>(a, count, st);
+    return mode == PAX_AX_PLAIN ? fev_launch<CW, NWARPS, MINB, PAX_AX_PLAIN>(a, count, st)
+                                : fev_launch<CW, NWARPS, MINB, PAX_AX_RESIDUAL>(a, count, st);
 }
 
 int pax_ax_fan_ev_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, cudaStream_t st)
@@ -557,16 +563,17 @@ int pax_ax_fan_ev_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count
     PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
     PAX_REQUIRE(p->fev_epoch >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
                                    "(the z travel of a single detector row exceeds its lanes)");
-    switch (p->fev_cw * 100 + p->fev_warps) {
-    case 404: return fev_launch_mode<4, 4>(a, mode, count, st);
-    case 408: return fev_launch_mode<4, 8>(a, mode, count, st);
-    case 804: return fev_launch_mode<8, 4>(a, mode, count, st);
-    case 808: return fev_launch_mode<8, 8>(a, mode, count, st);
-    case 1604: return fev_launch_mode<16, 4>(a, mode, count, st);
+    switch (p->fev_cw * 100 + p->fev_warps * 10 + p->fev_minb) {
+    case 482: return fev_launch_mode<4, 8, 2>(a, mode, count, st);
+    case 483: return fev_launch_mode<4, 8, 3>(a, mode, count, st);
+    case 484: return fev_launch_mode<4, 8, 4>(a, mode, count, st);
+    case 882: return fev_launch_mode<8, 8, 2>(a, mode, count, st);
+    case 844: return fev_launch_mode<8, 4, 4>(a, mode, count, st);
+    case 846: return fev_launch_mode<8, 4, 6>(a, mode, count, st);
     default: break;
     }
-    return pax_set_error(PAX_ERR_INVALID, "pax_ax: unsupported fan configuration CW=%d warps=%d", p->fev_cw,
-                         p->fev_warps);
+    return pax_set_error(PAX_ERR_INVALID, "pax_ax: unsupported fan configuration CW=%d warps=%d minb=%d", p->fev_cw,
+                         p->fev_warps, p->fev_minb);
 }
 
 // Epoch length, rows per warp and launch shape from the plan's geometry.
@@ -582,14 +589,16 @@ int pax_fan_ev_configure(PaxPlan *p)
         slope = std::fmax(slope, std::fmax(za, zb) / nmin);
     }
     const char *e;
-    int cw = 4, nw = 8;
+    int cw = 8, nw = 8;
     if ((e = getenv("PAX_FAN_CW")) && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16)) cw = atoi(e);   // tuning hooks
     if ((e = getenv("PAX_FAN_NW")) && (atoi(e) == 4 || atoi(e) == 8)) nw = atoi(e);
-    if (cw == 16) nw = 4;
+    int minb = nw == 8 ? 2 : 4;
+    if ((e = getenv("PAX_FAN_MINB")) && atoi(e) >= 1) minb = atoi(e);
+    p->fev_minb = minb;
     // a single row must fit the 32 lanes (128 slices) of a pass over one epoch, with room to spare for its
     // neighbours: halve the epoch until its z travel is at most 64 slices
-    int ep = 128;
-    if ((e = getenv("PAX_FAN_EPOCH")) && atoi(e) >= cw) ep = atoi(e) / cw * cw;
+    int ep = FAN_EPMAX;
+    if ((e = getenv("PAX_FAN_EPOCH")) && atoi(e) >= cw && atoi(e) <= FAN_EPMAX) ep = atoi(e) / cw * cw;
     while (ep >= cw && ep * slope > 64.0) ep /= 2;
     if (ep < cw) ep = 0;
     else ep = ep / cw * cw;

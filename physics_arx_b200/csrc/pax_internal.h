@@ -50,6 +50,7 @@ struct PaxPlan {
     int fev_epoch;              // steps per epoch (0: the kernel does not fit the geometry)
     int fev_cw;                 // steps per window (ring depth)
     int fev_warps;              // warps per CTA
+    int fev_minb;               // CTAs per SM the kernel is compiled for
 };
 
 
