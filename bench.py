@@ -39,10 +39,9 @@ def get_config(name):
     return cfg
 
 
-def describe(cfg, n_gpus, shard="angles"):
+def describe(cfg, n_gpus):
+    """The workload, identically for both arms (the rank grid actually used is reported under `sharding`)."""
     geo = cfg["geo"]
-    if isinstance(shard, str):
-        shard = (n_gpus, 1)
     nsub = -(-len(cfg["angles"]) // cfg["blocksize"])
     return {
         "workload": f"{cfg['name']}: planning CT {int(geo.nVoxel[1])}x{int(geo.nVoxel[2])}x{int(geo.nVoxel[0])}, "
@@ -52,8 +51,8 @@ def describe(cfg, n_gpus, shard="angles"):
         "niter": cfg["niter"], "blocksize": cfg["blocksize"], "I0": cfg["I0"], "sigma": cfg["sigma"],
         "accuracy": float(geo.accuracy),
         "parallelism": "1 GPU" if n_gpus == 1 else (
-            f"ranks in a {shard[0]} x {shard[1]} grid: the angles of each subset interleaved over {shard[0]} "
-            f"groups, the detector rows split in {shard[1]} bands") + ", volume replicated, NCCL all-reduce of the partial update per subset",
+            f"{n_gpus} GPUs, one process each: the rays of every OS-SART subset sharded over the ranks, volume "
+            "replicated, partial volume updates summed over NVLink once per subset"),
         "l2": "per-step working set (projections + volumes, ~2.4 GB at C2) exceeds the 126 MB L2; no flush",
     }
 
@@ -113,6 +112,8 @@ def cpu_sample(cfg, n_sample_angles=4):
     from oracle import cpu_oracle
     from physics_arx_b200.phantom import lung_phantom
     cpu_oracle.build()
+    # every host core, explicitly: under torch.distributed.run the inherited OMP_NUM_THREADS is 1
+    cores = cpu_oracle.set_threads(os.cpu_count() or 1)
     geo, angles = cfg["geo"], cfg["angles"]
     n = len(angles)
     pick = np.linspace(0, n, n_sample_angles, endpoint=False).astype(int)
@@ -125,7 +126,6 @@ def cpu_sample(cfg, n_sample_angles=4):
     t_ax, t_atb = (t1 - t0) / len(pick), (t2 - t1) / len(pick)
     # one volume = 1 simulation Ax + niter * (Ax + Atb) over all angles (V set-up not counted)
     t_vol = n * t_ax + cfg["niter"] * n * (t_ax + t_atb)
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return {"value": 1.0 / t_vol, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"float64 oracle (oracle/oracle.c, OpenMP) Ax+Atb of {len(pick)} of the {n} angles at full "
                       f"{cfg['name']} size: {t_ax:.2f} s/angle Ax, {t_atb:.2f} s/angle Atb; extrapolated to "
@@ -155,6 +155,85 @@ def run_reference(args, cfg, rank):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------- multi-GPU parity (untimed)
+def parity_vs_single_gpu(group, rank, world):
+    """A small case (tests/test_multigpu.py's geometry) run sharded over the group -- once with the default
+    collective, once with the fused reduce+update kernel forced -- against the same case on rank 0 alone."""
+    import torch
+    import torch.distributed as dist
+    from physics_arx_b200.phantom import artifact_volume, lung_phantom, make_geometry
+    from physics_arx_b200.pipeline import SCBCTPipeline
+    geo = make_geometry((16, 40, 40), (10.0, 6.0, 6.0), (40, 72), (6.0, 4.0), off_detector=(0.0, -30.0))
+    angles = np.linspace(0, 2 * np.pi, 23)
+    ct = torch.from_numpy(lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)).cuda()
+    art = torch.from_numpy(artifact_volume(geo.nVoxel, seed=1)).cuda()
+    kw = dict(niter=3, blocksize=5, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=3)
+    single = SCBCTPipeline(geo, angles, **kw).run_device(ct, art).clone() if rank == 0 else None
+    out = {}
+    for name, fused in (("default", None), ("fused", True)):
+        try:
+            pipe = SCBCTPipeline(geo, angles, group=group, fused_update=fused, **kw)
+            got = pipe.run_device(ct, art).clone()
+            coll = "nccl all-reduce" if pipe.st.fused is None else "fused kernel, " + pipe.st.fused["kind"]
+            ref = got.clone()
+            dist.broadcast(ref, src=0, group=group)
+            same = torch.tensor([1 if torch.equal(got, ref) else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN, group=group)
+            entry = {"collective": coll, "grid": list(pipe.st.grid), "bit_identical_across_ranks": bool(same.item())}
+            if rank == 0:
+                hu = (got - single).abs().double() * 4095.0
+                entry.update(mean_hu=float(hu.mean().item()), max_hu=float(hu.max().item()))
+            out[name] = entry
+            del pipe
+        except Exception as e:                          # noqa: BLE001 -- report, do not hide
+            out[name] = {"error": repr(e)[:200]}
+    return out
+
+
+# ------------------------------------------------- BASELINE.json's other configurations (untimed region)
+def secondary_configs():
+    """C1 / C4 / C5 of BASELINE.json on one GPU, a fraction of a second each (parity cases, not the headline)."""
+    import torch
+    from physics_arx_b200.algorithms import ossart
+    from physics_arx_b200.drivers import (VariationBatch, config_c4, motion_projections, phase_volumes,
+                                          respiratory_phases)
+    from physics_arx_b200.phantom import artifact_volume, config_c1, lung_phantom
+    from physics_arx_b200.pipeline import SCBCTPipeline
+
+    def timed(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    cfg = config_c1()
+    geo, angles = cfg["geo"], cfg["angles"]
+    ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    art = artifact_volume(geo.nVoxel, seed=1)
+    ct_d, art_d = torch.from_numpy(ct).cuda(), torch.from_numpy(art).cuda()
+    out = {}
+    pipe = SCBCTPipeline(geo, angles, niter=cfg["niter"], blocksize=cfg["blocksize"], I0=cfg["I0"],
+                         sigma=cfg["sigma"], scatter_scale=0.5, seed=0)
+    out["c1_ms_per_volume"] = timed(lambda: pipe.run_device(ct_d, art_d))
+    out["c1_projector"] = pipe.plan.projector
+    c4 = config_c4()
+    vb = VariationBatch(geo, angles, niter=cfg["niter"], blocksize=cfg["blocksize"], sigma=cfg["sigma"])
+    n = len(c4["scatter_scales"]) * len(c4["I0s"]) * len(c4["strides"])
+    t = timed(lambda: vb.run(ct_d, art_d, c4["scatter_scales"], c4["I0s"], c4["strides"], to_numpy=False), reps=1)
+    out["c4_ms_per_variation"] = t / n
+    out["c4_variations"] = n
+    ph = respiratory_phases(len(angles))
+    pv = torch.from_numpy(phase_volumes(ct, float(geo.dVoxel[0]))).cuda()
+    out["c5_ms"] = timed(lambda: ossart(motion_projections(pv, ph, geo, angles), geo, angles, cfg["niter"],
+                                        blocksize=cfg["blocksize"]))
+    return out
+
+
 # ------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -165,6 +244,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the untimed C1/C4/C5 and multi-GPU parity legs")
     ap.add_argument("--shard", default="auto", choices=["auto", "grid", "angles", "rows"],
                     help="how a subset's rays are cut over the ranks (physics_arx_b200/dist.py)")
     args = ap.parse_args()
@@ -195,6 +275,10 @@ def main():
         group = dist.group.WORLD
     if args.gpus != world and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    parity = None
+    if world > 1 and not args.no_secondary:
+        parity = parity_vs_single_gpu(group, rank, world)
 
     geo, angles = cfg["geo"], cfg["angles"]
     ct_np = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
@@ -295,10 +379,13 @@ def main():
             "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": describe(cfg, world, pipe.st.grid),
-            "collective": (None if world == 1 else
-                           ("fused reduce + update + broadcast kernel over " + pipe.st.fused["kind"]
-                            if pipe.st.fused is not None else "NCCL all-reduce + local update kernel")),
+            "data": "synthetic", "config": describe(cfg, world),
+            "sharding": (None if world == 1 else {
+                "grid": list(pipe.st.grid), "mode": pipe.st.shard,
+                "meaning": "ranks as (angle groups) x (detector bands): the angles of every subset interleaved over "
+                           "the groups, each group splitting the detector into bands",
+                "collective": ("fused reduce + update + broadcast kernel over " + pipe.st.fused["kind"]
+                               if pipe.st.fused is not None else "NCCL all-reduce + local update kernel")}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": ("k_ax_fan<4,8,8,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"
@@ -318,6 +405,13 @@ def main():
                            "h2d_bytes_per_step": int(ct_host.numel() * 4 + art_host.numel() * 4),
                            "d2h_bytes_per_step": int(out_host.numel() * 4),
                            "api": "SCBCTPipeline.run_host (pinned host volumes in, host volume out)"}
+        if parity is not None:
+            line["parity_vs_1gpu"] = parity
+        if world == 1 and not args.no_secondary:
+            try:
+                line["secondary"] = secondary_configs()
+            except Exception as e:                      # noqa: BLE001 -- secondary legs never sink the headline
+                line["secondary"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample(cfg)
         print(json.dumps(line))

@@ -85,6 +85,9 @@ typedef struct PaxAxEpilogue {
 #define PAX_ATB_STORE 0
 #define PAX_ATB_ADD 1
 #define PAX_ATB_SART 2
+#define PAX_ATB_SART_MAX 64         /* most angles of one PAX_ATB_SART call (the kernel's angle table);
+                                       STORE / ADD take any count */
+#define PAX_MAX_PEERS 16            /* most ranks pax_sart_update_fused serves */
 typedef struct PaxAtbEpilogue {
     int32_t mode;
     int32_t noneg;
@@ -103,8 +106,9 @@ int pax_plan_n_angles(const PaxPlan *plan);
 /* Which forward-projector kernel pax_ax runs.  Both evaluate the same sums on the same sample
  * lattice (tigre.Ax 'interpolated') and agree to fp32 rounding:
  *   RAY  one thread per ray, one trilinear gather per sample (csrc/ax.cu)
- *   FAN  the rays of a detector column share their in-plane interpolation and are summed from
- *        prefix tables (csrc/ax_fan.cu); pays off when the detector rows are finer than the slices
+ *   FAN  the rays of a detector column share their in-plane interpolation; a row touches the shared
+ *        prefix sums only where it crosses a slice boundary (csrc/ax_fan_ev.cu); pays off when the
+ *        detector rows are finer than the slices
  *   AUTO (default) FAN when the geometry makes the sharing worthwhile, else RAY.
  * pax_plan_projector returns the kernel AUTO resolves to (or the forced one). */
 #define PAX_PROJECTOR_AUTO 0
@@ -112,12 +116,13 @@ int pax_plan_n_angles(const PaxPlan *plan);
 #define PAX_PROJECTOR_FAN 2
 int pax_plan_set_projector(PaxPlan *plan, int kind);
 int pax_plan_projector(const PaxPlan *plan);
-/* tuning facts of the FAN kernel for this geometry: most detector rows that are summed from one set of
- * tables (0 = the kernel does not fit), warps per CTA, mean length in rows of the runs that share one
- * lattice */
+/* tuning facts of the FAN kernel for this geometry: detector rows whose z range fits the 32 lanes of a
+ * warp over one epoch in the worst case (0 = the kernel does not fit), warps per CTA, mean length in rows
+ * of the runs that share one lattice */
 int pax_plan_fan_info(const PaxPlan *plan, int *rows_per_tile, int *warps, double *mean_run);
-/* self-check of the FAN kernel: 1 if any launch so far met a z window wider than its 32 lanes (the
- * row tile is derived so that this cannot happen); synchronises the device */
+/* self-check of the FAN kernel: 1 if any launch so far met a single detector row whose z range over an
+ * epoch is wider than its 32 lanes (the epoch length is derived so that this cannot happen; the results
+ * of such a launch are wrong); synchronises the device */
 int pax_plan_fault(const PaxPlan *plan);
 
 /* Resident volume layout ("z-column": (Y+2, X+2, Zp) floats, z fastest, zero rim).

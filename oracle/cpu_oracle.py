@@ -57,12 +57,19 @@ def _load():
         lib.oracle_rescale_intensity.argtypes = [_dp, ctypes.c_long, ctypes.c_double, ctypes.c_double, _dp]
         lib.oracle_plahe.argtypes = [_dp, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long,
                                      ctypes.c_double, ctypes.c_double, _dp]
+        lib.oracle_set_threads.argtypes = [ctypes.c_int]
+        lib.oracle_set_threads.restype = ctypes.c_int
         for f in (lib.oracle_ax_interp, lib.oracle_atb_fdk, lib.oracle_raylen_w,
                   lib.oracle_philox, lib.oracle_ctnoise, lib.oracle_sart_update,
                   lib.oracle_resample_linear, lib.oracle_rescale_intensity, lib.oracle_plahe):
             f.restype = None
         _lib = lib
     return _lib
+
+
+def set_threads(n=None):
+    """Run the oracle's OpenMP loops on n threads (default: every host core); returns the count in effect."""
+    return int(_load().oracle_set_threads(int(n if n else (os.cpu_count() or 1))))
 
 
 def _p(a):

@@ -30,6 +30,22 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* Thread count of the OpenMP loops below (bench.py's CPU legs set it explicitly: a launcher such as
+ * torch.distributed.run exports OMP_NUM_THREADS=1).  Returns the count in effect. */
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 #define G_NZ 0
 #define G_NY 1
 #define G_NX 2

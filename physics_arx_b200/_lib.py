@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpax.so")
 PAX_AX_PLAIN, PAX_AX_RESIDUAL = 0, 1
 PAX_ATB_STORE, PAX_ATB_ADD, PAX_ATB_SART = 0, 1, 2
 PAX_PROJECTOR_AUTO, PAX_PROJECTOR_RAY, PAX_PROJECTOR_FAN = 0, 1, 2
+PAX_ATB_SART_MAX = 64
+PAX_MAX_PEERS = 16
 ANGLE_STRIDE = 8
 
 c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -134,13 +134,18 @@ class OSSARTState:
         # PAX_FUSED_UPDATE: unset -> on from 8 ranks up (measured: 0.38 vs 0.47 ms per subset at C2 on 8 GPUs,
         # but 0.05 ms slower than NCCL on 2); "0" off; "1" on (multicast when the fabric has it); "p2p" on, with
         # peer pointers
+        import torch.distributed as dist
         mode = os.environ.get("PAX_FUSED_UPDATE", "")
         if not required and (mode == "0" or (mode == "" and self.world < 8)):
             return
+        if self.world > _lib.PAX_MAX_PEERS:        # the kernel's peer table (csrc/plan.cu); larger domains use NCCL
+            if required:
+                raise ValueError(f"fused update supports at most {_lib.PAX_MAX_PEERS} ranks, got {self.world}")
+            return
+        g = self.group if self.group is not None else dist.group.WORLD
+        ok = 1
         try:
-            import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
-            g = self.group if self.group is not None else dist.group.WORLD
             if dist.get_backend(g) != "nccl":
                 raise RuntimeError("fused update needs the nccl backend")
             n = self.plan.vol_elems
@@ -162,8 +167,20 @@ class OSSARTState:
         except Exception as e:                     # noqa: BLE001 -- any failure means "not available here"
             if required:
                 raise
+            ok = 0
             self.fused = None
             self.fused_error = repr(e)
+        # every rank must take the same path: a rank that fell back would sit in all_reduce while the
+        # others wait in the symmetric-memory barrier
+        try:
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g)
+            if int(flag.item()) == 0 and self.fused is not None:
+                self.fused = None
+                self.fused_error = "another rank could not set up symmetric memory"
+                self.upd = self.plan.new_volume()
+        except Exception:                          # noqa: BLE001 -- no working collective: nothing to agree on
+            pass
 
     def new_iterate(self):
         """Zeroed resident volume for x.  With the fused collective it is THE symmetric buffer the peers
@@ -190,8 +207,18 @@ class OSSARTState:
                 self.kernel_events.append((ev[0], ev[1], count))
             self.launches += p.ax_launches(1)                  # (quad re-pack +) projector
         if self.world == 1:
-            p.atb(self.resid, first, count, x_res, _lib.PAX_ATB_SART, self.inv_v[s], lam, noneg)
-            self.launches += 1
+            if count <= _lib.PAX_ATB_SART_MAX:
+                p.atb(self.resid, first, count, x_res, _lib.PAX_ATB_SART, self.inv_v[s], lam, noneg)
+                self.launches += 1
+            else:
+                # a block larger than the fused kernel's angle table (TIGRE takes any blocksize, SIRT
+                # included): backproject into a scratch update (STORE, then ADD chunks inside pax_atb)
+                # and apply the update separately -- the path the multi-GPU branch below always takes
+                if self.upd is None:
+                    self.upd = p.new_volume()
+                p.atb(self.resid, first, count, self.upd, _lib.PAX_ATB_STORE)
+                p.sart_update(x_res, self.upd, self.inv_v[s], lam, noneg)
+                self.launches += 1 + -(-count // _lib.PAX_ATB_SART_MAX)
             return
         if count:
             p.atb(self.resid, first, count, self.upd, _lib.PAX_ATB_STORE)
@@ -266,10 +293,31 @@ def ossart(proj, geo, angles, niter, **kwargs):
         raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
     import torch.distributed as dist
 
-    dev = torch.device("cuda", _device_from_gpuids(gpuids))
-    b, was_np = _to_cuda(proj, dev, "proj")
     nang = np.asarray(angles).shape[0]
     nv, nu = (int(v) for v in geo.nDetector)
+    from ..projector import _multi
+    devs = _multi(gpuids)
+    if devs is not None and not any(k in state_kw for k in ("group", "distributed")):
+        # several devices in ONE process (what TIGRE does with such a gpuids; reference :31,:103)
+        if isinstance(proj, np.ndarray) and proj.dtype != np.float32:
+            raise TypeError(f"proj must be float32, got {proj.dtype}")
+        if isinstance(proj, torch.Tensor) and proj.dtype != torch.float32:
+            raise TypeError(f"proj must be float32, got {proj.dtype}")
+        if tuple(proj.shape) != (nang, nv, nu):
+            raise ValueError(f"proj shape {tuple(proj.shape)} != (N, *geo.nDetector) {(nang, nv, nu)}")
+        if isinstance(init, str):
+            raise NotImplementedError(f"init={init!r} is not on this path (reference uses the default, zeros)")
+        from ..multidev import MultiDevice
+        md = MultiDevice(geo, angles, devs, blocksize=blocksize, OrderStrategy=order)
+        x0 = None if init is None else _to_cuda(init, md.devices[0], "init")[0]
+        res = md.ossart(proj, niter, lmbda, lmbda_red, noneg, x0, state_kw.get("w_variant", "matlab"),
+                        state_kw.get("v_variant", "A"), computel2, verbose)
+        was_np = isinstance(proj, np.ndarray)
+        if computel2:
+            return (res[0].cpu().numpy() if was_np else res[0]), res[1]
+        return res.cpu().numpy() if was_np else res
+    dev = torch.device("cuda", _device_from_gpuids(gpuids))
+    b, was_np = _to_cuda(proj, dev, "proj")
     if tuple(b.shape) != (nang, nv, nu):
         raise ValueError(f"proj shape {tuple(b.shape)} != (N, *geo.nDetector) {(nang, nv, nu)}")
     st = OSSARTState(b, geo, angles, blocksize, order, **state_kw)
@@ -296,6 +344,7 @@ def ossart(proj, geo, angles, niter, **kwargs):
             print(f"OS-SART iteration {it + 1}/{niter}, lambda={lam:.4f}")
         lam *= lmbda_red
     out = p.unpack(x)
+    p.check_fault()                    # the fan-plane projector's self-check (csrc/ax_fan_ev.cu)
     out = out.cpu().numpy() if was_np else out
     return (out, np.array(l2)) if computel2 else out
 

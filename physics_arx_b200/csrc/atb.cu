@@ -11,7 +11,7 @@
 #include "pax_internal.h"
 
 #define ATB_ZT 8
-#define ATB_MAX_ANGLES 64
+#define ATB_MAX_ANGLES PAX_ATB_SART_MAX
 
 struct AtbAngle {
     float cosv, sinv, DSD, DSO;

@@ -40,7 +40,7 @@
 #define FAN_MAXSEG 8            // runs (pieces of runs) packed into the lanes of one pass
 #define FAN_QCAP 96             // crossing events served per round
 #define FAN_MAXROWS 1024        // detector rows one warp walks
-#define FAN_EPMAX 128           // most steps per epoch
+#define FAN_EPMAX 256           // most steps per epoch
 
 template <int CW>
 struct __align__(16) FanEvSmem {
@@ -53,10 +53,11 @@ struct __align__(16) FanEvSmem {
     int4 s_i[FAN_MAXSEG];                      // per run: {first lane, lanes, first quad, last step of the epoch}
     float s_zrefv[FAN_MAXSEG];                 // per run: increment of z_ref per row
     int s_ra[FAN_MAXSEG], s_rb[FAN_MAXSEG], s_cls[FAN_MAXSEG], c_n[FAN_MAXSEG];
-    float rtab[FAN_EPMAX + 4];                 // rcp(step) of the epoch's steps (the crossing predicate)
+    float rtab[36];                            // rcp(step) at the epoch's window boundaries (the crossing predicate)
     unsigned queue[FAN_QCAP];
     unsigned char lane_seg[32];
     unsigned starts[FAN_MAXROWS / 32];         // bit r of word w: row 32w+r starts a run of equal n
+    int run_n[32];                             // n of the column's first 32 runs (more: recomputed on the fly)
 };
 
 // first row after `cur` that starts a new run (or nRows)
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
     const double vz = A.vz;
     const double dz0 = A.oz + (double)V0 * vz - sz;               // P_z - S_z of the band's row 0; +vz per row
     const float bq = (float)(dz0 / vz);                           // the predicate's b
+    const double rvz = 1.0 / vz;
     const int EP = a.fan_epoch;
     const size_t dx4 = (size_t)a.nzp * 4, dy4 = (size_t)a.nxp * a.nzp * 4;
     float r2 = 0.f, mymax = -INFINITY;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
     // ---- runs of rows with equal n (TIGRE's lattice); clear the rows' sums
     int nlo = INT_MAX, nhi = 0;
     {
-        int last = -2;
+        int last = -2, nruns = 0;
         for (int r0 = 0; r0 < nRows; r0 += 32) {
             const bool in = r0 + lane < nRows;
             const double dz = dz0 + (double)(r0 + lane) * vz;
@@ -166,8 +168,12 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
             if (in) { nlo = min(nlo, n); nhi = max(nhi, n); rsum[r0 + lane] = 0.f; }
             int prev = __shfl_up_sync(0xffffffffu, n, 1);
             if (lane == 0) prev = last;
-            const unsigned m = __ballot_sync(0xffffffffu, in && n != prev);
+            const bool st = in && n != prev;
+            const unsigned m = __ballot_sync(0xffffffffu, st);
             if (lane == 0) sm.starts[r0 >> 5] = m;
+            const int ord = nruns + __popc(m & ((1u << lane) - 1u));
+            if (st && ord < 32) sm.run_n[ord] = n;
+            nruns += __popc(m);
             last = __shfl_sync(0xffffffffu, n, 31);
         }
         nlo = __reduce_min_sync(0xffffffffu, nlo);
@@ -188,8 +194,8 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
             const int e1 = min(e0 + EP - 1, Emax);
             const int ref = e0 + (EP >> 1);
             const int nwin = (e1 - e0 + CW) / CW;
-            for (int t = lane; t <= EP; t += 32) sm.rtab[t] = fev_rcp_step(e0 + t);
-            int cur = 0;
+            if (lane <= nwin) sm.rtab[lane] = fev_rcp_step(e0 + lane * CW);   // nwin <= 32 (pax_fan_ev_configure)
+            int cur = 0, ri = 0;                                  // row, and the ordinal of the run it is in
 #pragma unroll 1
             while (cur < nRows) {
                 // ================= pack runs (or pieces of runs) into the lanes of one pass (uniform over the warp)
@@ -197,11 +203,15 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
 #pragma unroll 1
                 while (cur < nRows && nseg < FAN_MAXSEG && used < 31) {
                     const int e = fev_next_start(sm.starts, cur, nRows);
-                    const double dzc = dz0 + (double)cur * vz;
-                    const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
+                    int nrun;
+                    if (ri < 32) nrun = sm.run_n[ri];
+                    else {
+                        const double dzc = dz0 + (double)cur * vz;
+                        nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
+                    }
                     const int I0 = max((int)ceil(lam0 * (double)nrun), 0), I1 = (int)floor(lam1 * (double)nrun);
                     const int ja = max(I0, e0), jb = min(I1, e1);
-                    if (ja > jb) { cur = e; continue; }           // the run has no sample in this epoch
+                    if (ja > jb) { cur = e; ++ri; continue; }     // the run has no sample in this epoch
                     const double rn = 1.0 / (double)nrun;
                     const float s0f = (float)(dz0 * rn), zvrf = (float)(vz * rn);
                     const float fa = (float)ja, fb = (float)jb;
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
                         const int g = nseg;
                         sm.s_ra[g] = cur; sm.s_rb[g] = rb; sm.s_cls[g] = cls;
                         sm.s_i[g] = make_int4(used, nq, qa, jb);
-                        sm.s_f[g] = make_float4((float)((double)nrun / vz), s0f, zvrf, (float)(sz + (double)ref * dz0 * rn));
+                        sm.s_f[g] = make_float4((float)((double)nrun * rvz), s0f, zvrf, (float)(sz + (double)ref * dz0 * rn));
                         sm.s_zrefv[g] = (float)((double)ref * vz * rn);
                         if (cls == ncls) {
                             // in-plane origin of the epoch, split in double into an integer cell and a fraction; steps
@@ -258,6 +268,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
                     used += nq;
                     ++nseg;
                     cur = rb;
+                    if (rb == e) ++ri;
                 }
                 if (nseg == 0) continue;
 
@@ -336,9 +347,11 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
 #pragma unroll 1
                 for (int m = 0; m < nwin; ++m) {
                     const int w0 = e0 + m * CW;
-                    const float *rt = sm.rtab + m * CW;            // rt[t] = rcp(w0 + t)
                     if (m) { fill_w(w0 + 1, CW, 0); __syncwarp(); }
                     // ---- CW steps: running (A, C) of my four slices into the ring
+                    const int iend = min(w0 + CW, e1);
+                    int lo0 = 0, lo1 = 0, lo2 = 0, lo3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0, mine = 0, incl = 0;
+                    unsigned up = 0;
 #pragma unroll
                     for (int t = 0; t < CW; ++t) {
                         const float4 wn = wp[t];                   // the next step
@@ -365,14 +378,13 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
                     }
                     __syncwarp();
                     // ---- crossings at steps w0+1 .. iend (prefix through the step before, i.e. ring row t-1)
-                    const int iend = min(w0 + CW, e1);
-                    int lo0, lo1, lo2, lo3, n0, n1, n2, n3;
-                    unsigned up = 0;
                     {
                         const int il = min(iend, segjb);
                         int c0 = cs0, c1 = cs1, c2 = cs2, c3 = cs3;
                         if (on && il > w0) {
-                            const float re = rt[il - w0];
+                            // (the predicate's reciprocal: tabulated at the window boundaries, else -- the run's
+                            // last window -- computed by the same function)
+                            const float re = (il == w0 + CW) ? sm.rtab[m + 1] : fev_rcp_step(il);
                             c0 = min(max(fev_cv(ak0, re, bq), segra), segrb); c1 = min(max(fev_cv(ak1, re, bq), segra), segrb);
                             c2 = min(max(fev_cv(ak2, re, bq), segra), segrb); c3 = min(max(fev_cv(ak3, re, bq), segra), segrb);
                         }
@@ -381,9 +393,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
                         lo2 = min(c2, cs2); n2 = abs(c2 - cs2); up |= (c2 < cs2) ? 0x20000000u : 0u;
                         lo3 = min(c3, cs3); n3 = abs(c3 - cs3); up |= (c3 < cs3) ? 0x10000000u : 0u;
                         cs0 = c0; cs1 = c1; cs2 = c2; cs3 = c3;
+                        mine = n0 + n1 + n2 + n3;
+                        incl = mine;
                     }
-                    const int mine = n0 + n1 + n2 + n3;
-                    int incl = mine;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const int o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_ev(const AxArgs a)
                         const float4 sf = sm.s_f[g];
                         const float zrv = sm.s_zrefv[g];
                         // the run's last step of the epoch; the sums do not change after it (G = 0)
-                        const float re = sm.rtab[si.w - e0], fe = (float)si.w;
+                        const float re = fev_rcp_step(si.w), fe = (float)si.w;
                         const int k0 = 4 * si.z;
                         for (int v = sm.s_ra[g] + lane; v < sm.s_rb[g]; v += 32) {
                             const float fv = (float)v;
@@ -566,10 +578,10 @@ int pax_ax_fan_ev_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count
     switch (p->fev_cw * 100 + p->fev_warps * 10 + p->fev_minb) {
     case 482: return fev_launch_mode<4, 8, 2>(a, mode, count, st);
     case 483: return fev_launch_mode<4, 8, 3>(a, mode, count, st);
-    case 484: return fev_launch_mode<4, 8, 4>(a, mode, count, st);
     case 882: return fev_launch_mode<8, 8, 2>(a, mode, count, st);
     case 844: return fev_launch_mode<8, 4, 4>(a, mode, count, st);
-    case 846: return fev_launch_mode<8, 4, 6>(a, mode, count, st);
+    case 445: return fev_launch_mode<4, 4, 5>(a, mode, count, st);
+    case 444: return fev_launch_mode<4, 4, 4>(a, mode, count, st);
     default: break;
     }
     return pax_set_error(PAX_ERR_INVALID, "pax_ax: unsupported fan configuration CW=%d warps=%d minb=%d", p->fev_cw,
@@ -589,7 +601,7 @@ int pax_fan_ev_configure(PaxPlan *p)
         slope = std::fmax(slope, std::fmax(za, zb) / nmin);
     }
     const char *e;
-    int cw = 8, nw = 8;
+    int cw = 8, nw = 4;
     if ((e = getenv("PAX_FAN_CW")) && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16)) cw = atoi(e);   // tuning hooks
     if ((e = getenv("PAX_FAN_NW")) && (atoi(e) == 4 || atoi(e) == 8)) nw = atoi(e);
     int minb = nw == 8 ? 2 : 4;
@@ -597,8 +609,9 @@ int pax_fan_ev_configure(PaxPlan *p)
     p->fev_minb = minb;
     // a single row must fit the 32 lanes (128 slices) of a pass over one epoch, with room to spare for its
     // neighbours: halve the epoch until its z travel is at most 64 slices
-    int ep = FAN_EPMAX;
+    int ep = 128;
     if ((e = getenv("PAX_FAN_EPOCH")) && atoi(e) >= cw && atoi(e) <= FAN_EPMAX) ep = atoi(e) / cw * cw;
+    if (ep > 32 * cw) ep = 32 * cw;                             // at most 32 windows per epoch (rtab)
     while (ep >= cw && ep * slope > 64.0) ep /= 2;
     if (ep < cw) ep = 0;
     else ep = ep / cw * cw;

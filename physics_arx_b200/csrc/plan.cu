@@ -276,7 +276,6 @@ extern "C" int pax_sart_update(const PaxPlan *p, float *x_res, const float *upd_
 // Measured on 8 x B200 at C2 (tools/bench_collective.py): all-reduce + update kernel 0.472 ms, this kernel
 // with its two barriers 0.381 ms (multicast) / 0.448 ms (peer pointers); four units per thread: 0.413 ms;
 // a __threadfence_system() per thread: +0.2 ms.  On 2 GPUs it is 0.05 ms slower than NCCL.
-#define PAX_MAX_PEERS 16
 struct PeerPtrs {
     float *x[PAX_MAX_PEERS];
     const float *upd[PAX_MAX_PEERS];

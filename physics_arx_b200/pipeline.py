@@ -25,7 +25,7 @@ from .projector import _ptr, _stream
 class SCBCTPipeline:
     def __init__(self, geo, angles, niter=20, blocksize=20, I0=1e8, sigma=4.0, scatter_scale=1.0,
                  lmbda=1.0, lmbda_red=0.99, seed=0, group=None, device=None, w_variant="matlab",
-                 v_variant="A", shard="auto"):
+                 v_variant="A", shard="auto", fused_update=None):
         if not torch.cuda.is_available():
             raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
@@ -40,7 +40,7 @@ class SCBCTPipeline:
         with torch.cuda.device(self.device):
             self.st = OSSARTState(None, geo, self.angles, blocksize, None, w_variant=w_variant,
                                   v_variant=v_variant, group=group, distributed=group is not None,
-                                  device=self.device.index, shard=shard)
+                                  device=self.device.index, shard=shard, fused_update=fused_update)
         st = self.st
         self.plan = st.plan
         self.n_local = int(st.b.shape[0])
@@ -118,6 +118,7 @@ class SCBCTPipeline:
         self.launches += st.launches - n0
         p.unpack(self.x_res, out=self.out)
         self.launches += 1
+        p.check_fault()                # covers simulate() as well: same plan, sticky flag
         return self.out
 
     # ------------------------------------------------------------- entry points

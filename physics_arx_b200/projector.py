@@ -29,14 +29,25 @@ def _ptr(t):
 
 
 def _device_from_gpuids(gpuids):
+    """First device a ``gpuids`` argument names (calls that list several go through multidev.MultiDevice)."""
     if gpuids is None:
         return torch.cuda.current_device()
     devices = getattr(gpuids, "devices", gpuids)
-    if isinstance(devices, (list, tuple)):
+    if isinstance(devices, (list, tuple, range)):
         if len(devices) == 0:
             raise ValueError("gpuids is empty")
         return int(devices[0])
     return int(devices)
+
+
+def _multi(gpuids):
+    """The device list if ``gpuids`` names more than one device (TIGRE splits such a call over all of them,
+    reference :31,86,103), else None."""
+    if gpuids is None:
+        return None
+    from .multidev import devices_of
+    devs = devices_of(gpuids)
+    return devs if len(devs) > 1 else None
 
 
 class Plan:
@@ -104,6 +115,13 @@ class Plan:
     def fault(self):
         """1 if the fan kernel ever met a z window wider than its lanes on this plan (self-check)."""
         return int(self.lib.pax_plan_fault(self._h))
+
+    def check_fault(self):
+        """Raise if the fan-plane projector flagged a launch whose z range did not fit its lanes (the results
+        of such a launch are wrong; pax_fan_ev_configure is meant to rule it out).  Synchronises the device."""
+        if self.projector == "fan" and self.fault():
+            raise _lib.PaxError("the fan-plane projector met a detector row whose z range does not fit its lanes "
+                                "on this geometry; use projector='ray' (PAX_AX_KERNEL=ray)")
 
     def ax_launches(self, channels=1):
         """kernels one pax_ax call launches (bench.py's gpu_launches claim)."""
@@ -275,6 +293,16 @@ def Ax(img, geo, angles, projection_type="interpolated", **kwargs):
         raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
     dev = torch.device("cuda", _device_from_gpuids(kwargs.get("gpuids")))
     vol, was_np = _to_cuda(img, dev, "img")
+    devs = _multi(kwargs.get("gpuids"))
+    if devs is not None and kwargs.get("plan") is None:
+        from .multidev import MultiDevice
+        md = MultiDevice(geo, angles, devs)
+        md.plans[0]._check_vol(vol)
+        art_t, a1 = None, 0.0
+        if kwargs.get("scatter") is not None:
+            art, a1 = kwargs["scatter"]
+            art_t, _ = _to_cuda(art, vol.device, "scatter volume")
+        return md.gather_projections(md.ax(vol, art_t, a1), was_np)
     plan = kwargs.get("plan") or Plan(geo, angles, device=vol.device.index)
     res0 = plan.pack(vol)
     res1, a1 = None, 0.0
@@ -293,6 +321,19 @@ def Atb(projections, geo, angles, backprojection_type="FDK", **kwargs):
                          "(only 'FDK', the weights ossart uses)")
     if not torch.cuda.is_available():
         raise _lib.PaxError("no CUDA device: physics_arx_b200 has no CPU fallback")
+    devs = _multi(kwargs.get("gpuids"))
+    if devs is not None and kwargs.get("plan") is None:
+        if isinstance(projections, np.ndarray) and projections.dtype != np.float32:
+            raise TypeError(f"projections must be float32, got {projections.dtype}")
+        if isinstance(projections, torch.Tensor) and projections.dtype != torch.float32:
+            raise TypeError(f"projections must be float32, got {projections.dtype}")
+        from .multidev import MultiDevice
+        md = MultiDevice(geo, angles, devs)
+        want = (md.n,) + tuple(int(v) for v in geo.nDetector)
+        if tuple(projections.shape) != want:
+            raise ValueError(f"projections shape {tuple(projections.shape)} != (N, *geo.nDetector) {want}")
+        out = md.atb(projections)
+        return out.cpu().numpy() if isinstance(projections, np.ndarray) else out
     dev = torch.device("cuda", _device_from_gpuids(kwargs.get("gpuids")))
     proj, was_np = _to_cuda(projections, dev, "projections")
     plan = kwargs.get("plan") or Plan(geo, angles, device=proj.device.index)

@@ -86,3 +86,34 @@ def test_sharded_pipeline_equals_single_gpu(shard):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     print(sorted(res)[0][2])
+
+
+def test_gpuids_with_several_devices_in_one_process():
+    """The reference passes EVERY GPU of the first name as ``gpuids`` (pCT_CBCT_Reconstruction.py:31,86,103);
+    such a call is split over the devices inside one process (multidev.MultiDevice) and must give what one
+    device gives."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import physics_arx_b200 as pax
+    from physics_arx_b200.phantom import lung_phantom, make_geometry
+    from physics_arx_b200.utilities import gpu
+    ids = gpu.getGpuIds(gpu.getGpuNames()[0])
+    assert len(ids) >= 2
+    one = gpu.GpuIds(ids.name, ids.devices[:1])
+    geo = make_geometry((16, 40, 40), (10.0, 4.0, 4.0), (120, 72), (1.5, 4.0), off_detector=(0.0, -30.0))
+    angles = np.linspace(0, 2 * np.pi, 23)
+    vol = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    p1 = pax.Ax(vol, geo, angles, "interpolated", gpuids=one)
+    pn = pax.Ax(vol, geo, angles, "interpolated", gpuids=ids)
+    assert pn.shape == p1.shape and np.array_equal(pn, p1)          # same kernel, same angles: bit-identical
+    b1 = pax.Atb(p1, geo, angles, "FDK", gpuids=one)
+    bn = pax.Atb(p1, geo, angles, "FDK", gpuids=ids)
+    assert np.abs(bn - b1).max() <= 1e-5 * np.abs(b1).max()          # summation order over devices only
+    r1 = pax.algorithms.ossart(p1, geo, angles, 3, blocksize=5, gpuids=one)
+    rn, l2 = pax.algorithms.ossart(p1, geo, angles, 3, blocksize=5, gpuids=ids, computel2=True)
+    hu = np.abs(rn - r1) * 4095.0
+    print(f"{len(ids)} devices in one process vs one: mean {hu.mean():.2e} HU, max {hu.max():.2e} HU")
+    assert hu.mean() <= 0.05 and hu.max() <= 0.5
+    assert len(l2) == 3 and l2[-1] < l2[0]
