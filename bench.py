@@ -388,7 +388,7 @@ def main():
                                if pipe.st.fused is not None else "NCCL all-reduce + local update kernel")}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": ("k_ax_fan<4,8,8,RESIDUAL> (fan-plane projector, csrc/ax_fan.cu)"
+                         "kernel": ("k_ax_fan<8,4,4,RESIDUAL> (event-driven fan-plane projector, csrc/ax_fan.cu)"
                                     if pipe.plan.projector == "fan" else
                                     "k_ax<1,RESIDUAL,32> (ray-march projector, csrc/ax.cu)"),
                          "peak_source": peak_src, "avg_launch_ms": avg_ms,

@@ -344,7 +344,7 @@ def ossart(proj, geo, angles, niter, **kwargs):
             print(f"OS-SART iteration {it + 1}/{niter}, lambda={lam:.4f}")
         lam *= lmbda_red
     out = p.unpack(x)
-    p.check_fault()                    # the fan-plane projector's self-check (csrc/ax_fan_ev.cu)
+    p.check_fault()                    # the fan-plane projector's self-check (csrc/ax_fan.cu)
     out = out.cpu().numpy() if was_np else out
     return (out, np.array(l2)) if computel2 else out
 

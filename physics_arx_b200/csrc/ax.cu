@@ -354,7 +354,7 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
     a.a0 = epi->a0; a.a1 = epi->a1; a.c = epi->c;
     a.accumulate = 0;
     a.whx = epi->w_half_x; a.why = epi->w_half_y; a.whz = epi->w_half_z; a.wthr = epi->w_thr;
-    a.fan_rows = 0; a.fan_epoch = 0;
+    a.fan_rows = 0; a.fan_epoch = 0; a.fan_count = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (pax_plan_projector(p) == PAX_PROJECTOR_FAN) {
         // one channel per launch; a second channel is a first pass whose result the second adds to
@@ -364,14 +364,12 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
             a1.c = 0.f; a1.accumulate = 0;
             if (epi->out1) { a1.out = epi->out1; a1.a0 = 1.f; }
             else { a1.a0 = epi->a1; }
-            int rc = p->fan_impl ? pax_ax_fan_ev_launch(p, a1, PAX_AX_PLAIN, count, st)
-                                 : pax_ax_fan_launch(p, a1, PAX_AX_PLAIN, count, st);
+            int rc = pax_ax_fan_launch(p, a1, PAX_AX_PLAIN, count, st);
             if (rc != PAX_OK) return rc;
             a.accumulate = epi->out1 ? 0 : 1;
         }
         a.vol1 = nullptr; a.out1 = nullptr;
-        int rc = p->fan_impl ? pax_ax_fan_ev_launch(p, a, epi->mode, count, st)
-                             : pax_ax_fan_launch(p, a, epi->mode, count, st);
+        int rc = pax_ax_fan_launch(p, a, epi->mode, count, st);
         if (rc != PAX_OK) return rc;
         PAX_CHECK_CUDA(cudaGetLastError());
         return PAX_OK;

@@ -1,77 +1,63 @@
-// Fan-plane forward projector: tigre.Ax 'interpolated' (reference call site
-// pCT_CBCT_Reconstruction.py:86 and, inside ossart, :103; algorithm SURVEY.md A.3) evaluated on
-// TIGRE's own sample lattice, but with the work shared between the rays of a detector column.
+// Fan-plane forward projector, event-driven: tigre.Ax 'interpolated' (reference call site
+// pCT_CBCT_Reconstruction.py:86 and, inside ossart, :103; algorithm SURVEY.md A.3) on TIGRE's own sample
+// lattice, with the in-plane half of the trilinear interpolation shared by all rays of a detector column
+// AND the rows touching the shared tables only when they cross a slice boundary.
 //
-// Why it can be shared.  Pixel (v,u) of one projection is at P = O + u*U + v*V with V = z-hat, so
-// all rays of a detector COLUMN u lie in one vertical plane through the source and share the
-// in-plane chord S_xy -> P_xy.  TIGRE samples ray (u,v) at q_i = S + i*(P-S)/n, n = ceil(|P-S|/acc):
-// the in-plane positions q_i,xy = S_xy + i*(P_xy-S_xy)/n depend on the row v ONLY through the
-// integer n(v), which is constant over long runs of rows when the detector is finer than the
-// slices (C2: 768 rows, 3..4 distinct n per column).  For a run of rows with equal n
-//   sample(i, v) = (1-t) * G_i(k) + t * G_i(k+1),   k = floor(z_i(v)),  t = z_i(v) - k,
-//   G_i(k)       = bilinear_xy(volume slice k) at q_i,xy          -- one value per (step, slice),
-// i.e. the in-plane half of the trilinear interpolation is done once per (step, slice) instead of
-// once per (step, row): ~8x fewer gathers at C2 (768 rows look at ~90 slices).
+// Sharing.  The rays of a detector column u lie in one vertical plane through the source;
+// rows with equal n = ceil(|P-S|/accuracy) (a "run") share the in-plane sample positions, so
+//   sample(i, v) = (1-t) G_i(k) + t G_i(k+1),  k = floor(z_i(v)), t = z_i(v) - k,  G_i(k) = bilinear_xy(slice k).
 //
-// Rays are nearly horizontal (|dz| per step <= 0.02 slices at C2), so a ray stays in one slice
-// pair (k,k+1) for tens of steps, during which t is LINEAR in the step index.  With the running
-// sums  P_k(j) = sum_{i<j} G_i(k)  and  Q_k(j) = sum_{i<j} (i-j0) G_i(k)  of a block of steps,
-//   sum_{i=a..b} sample(i,v) = dP_k + alpha*(dP_{k+1} - dP_k) + delta*(dQ_{k+1} - dQ_k)
-// (alpha, delta = intercept and slope of t over the stretch), so a row costs four table look-ups
-// per stretch instead of one trilinear sample per step.  The sums are exactly TIGRE's Riemann sum
-// re-associated; only fp32 rounding differs (measured ~1e-7 relative L2 against the float64 oracle).
+// Events.  With running sums over the steps of an epoch,  A_k(j) = sum_{i<=j} G_i(k),
+// C_k(j) = sum_{i<=j} (i - ref) G_i(k), the sum of a row over the steps it spends in slice pair (k,k+1) is a
+// difference of  f_k(j) = A_k + tau_k (A_{k+1} - A_k) + s (C_{k+1} - C_k)   (tau_k = z_ref(v) - k, s = dz per step),
+// and the differences telescope: the line integral of row v over an epoch is
+//   f_K(last step)  -  sum over crossings of a boundary k at step j of  dir * (tau_k D2A_k(j-1) + s D2C_k(j-1)),
+//   D2X_k = X_{k-1} - 2 X_k + X_{k+1},  dir = +1 upwards.
+// A row costs one table look-up per slice-boundary crossing (~10 per ray at C2) and one per epoch, instead of
+// one trilinear sample per step (~1000).  The sums are
+// TIGRE's Riemann sum re-associated; only fp32 rounding differs (tools/fan_event_model.py: 2e-7 relative L2 at
+// epochs of 256 steps).
 //
-// Kernel shape (sm_100a, no tensor cores: this is a gather plus prefix sums).  Every WARP works on
-// its own detector column (one angle, one u, a tile of <= 256 rows) with its own tables in shared memory;
-// there is no CTA-wide barrier, so the gather-heavy and the table-heavy phases of different warps
-// overlap on an SM.  Per run of equal n the warp walks the chord in chunks of G*8 steps:
-//   phase 0  once per chunk: a lane prepares one or two steps -- in-plane cell offset and the four
-//            bilinear weights (chunk origin split into integer cell + fraction in double, steps added
-//            in fp32, so nothing accumulates along the ray);
-//   groups   the rows of the run are cut, for THIS chunk, into groups whose z extent over the chunk fits
-//            the 4*LQ slices the lanes of a stream cover (closed form: z is linear in row and step);
-//   phase 1  per group: the warp advances G streams of 8 consecutive steps at once; a lane owns one
-//            stream and four consecutive slices of the group's z window (the resident volume is
-//            z-fastest, so a corner of a step is one 16-byte load per lane), accumulates P and Q down
-//            its stream and writes them to the table; a shuffle scan over the streams gives each its
-//            carry.  Loads are predicated (same cell: no load) and issued two steps ahead into two
-//            alternating register sets;
-//   phase 2  per group: a lane owns two detector rows at a time and adds up their stretches from the
-//            table (+ carry); the rows' running sums live in shared memory across chunks.
-// pax_fan_configure checks from the geometry that at least one row always fits (else the kernel is not
-// offered) and estimates how many do (AUTO's criterion).
+// "Row v is above boundary k at step i" is DEFINED as  v >= ceil(fma(a_k, rcp(i), -b)),  a_k = (k - sz) n / vz,
+// b = dz0 / vz.  It is monotone in i and in k by construction (correctly rounded operations are monotone),
+// so the crossings enumerated per boundary and the pair found at an epoch's end always agree; that it differs
+// from the exact predicate by ~1e-5 slices is harmless, the interpolant being continuous across a boundary.
+//
+// Kernel shape (sm_100a; a gather plus prefix sums, no tensor cores).  One WARP owns one detector column
+// (angle, u, up to FAN_MAXROWS rows).  A lane owns four consecutive slices (one 16-byte load per bilinear
+// corner: the resident volume is z-fastest) of one run; the lanes of a warp are packed, per epoch, with the
+// z ranges the runs of the column look at (greedy; what does not fit 32 lanes goes to a second pass).  Per step
+// a lane does 4 predicated LDG.128 (no load while the in-plane cell is unchanged), 8 packed FMAs for G, 4 packed
+// accumulates and 2 STS.128 of its running (A, C) into a ring of CW steps.  After every CW steps the lanes
+// enumerate the rows that crossed their boundaries (closed form: a row interval per boundary), and the warp
+// serves those events 32 at a time from the ring; at the end of an epoch every row reads its pair once.
 #include <climits>
 #include <cmath>
 #include <cstdlib>
 
 #include "pax_internal.h"
 
-#define FAN_NW 8            // warps per CTA (independent; the CTA only groups adjacent columns for L1)
-#define FAN_GROUP 128       // most rows summed from one set of tables
-#define FAN_MAXTILE 256     // detector rows one warp walks (their sums and run-start masks live in smem)
+#define FAN_MAXSEG 8            // runs (pieces of runs) packed into the lanes of one pass
+#define FAN_QCAP 96             // crossing events served per round
+#define FAN_MAXROWS 1024        // detector rows one warp walks
+#define FAN_EPMAX 256           // most steps per epoch
 
-// LQ lanes (z quads) per step, SB steps per stream
-template <int LQ, int SB>
-struct FanCfg {
-    static constexpr int W = 4 * LQ;            // slices of a z window
-    static constexpr int G = 32 / LQ;           // streams a warp advances at once
-    static constexpr int B = SB;
-    static constexpr int LOGB = SB == 16 ? 4 : 3;
-    static constexpr int CW = G * SB;           // steps per chunk
-    static constexpr int TS = W + 2;            // table row stride in float2 (rows stay 16-byte aligned)
-    static constexpr int TROWS = CW + G;        // one spare row per stream (bank skew)
-};
-
-template <int LQ, int SB>
-struct __align__(16) FanWarpSmem {
-    using Cfg = FanCfg<LQ, SB>;
-    float2 T[Cfg::TROWS * Cfg::TS];             // stream-local running (P,Q) per (step, slice)
-    float2 carry[Cfg::G * Cfg::TS];             // (P,Q) of all earlier streams of the chunk
-    float2 total[Cfg::TS];                      // (P,Q) of the whole chunk
-    float4 w[Cfg::TROWS];                       // per step (stream-padded): three bilinear weights (the fourth
-                                                // is 1 - their sum) and the in-plane cell's byte offset
-    unsigned starts[FAN_MAXTILE / 32];          // bit r of word w: row 32w+r starts a run of equal n
-    float rsum[FAN_MAXTILE];                    // running line integral of every row of the tile
+template <int CW>
+struct __align__(16) FanSmem {
+    float ring[CW * 256 + 8];                  // 4 guard floats, then [step][A of the 128 lane slices | C of them]
+    float4 w[FAN_MAXSEG][CW + 1];              // per lattice (distinct n): three bilinear weights + cell offset of the
+                                               // steps w0+1 .. w0+CW of the window (slot CW: the epoch's first step)
+    float4 c_geo[FAN_MAXSEG];                  // per lattice: {ddx, ddy, fraction x, fraction y} of the epoch's origin
+    int4 c_cell[FAN_MAXSEG];                   // per lattice: {origin cell x, y, first step, last step} of the epoch
+    float4 s_f[FAN_MAXSEG];                    // per run: {n / vz, dz per step of row 0, its increment per row, z_ref of row 0}
+    int4 s_i[FAN_MAXSEG];                      // per run: {first lane, lanes, first quad, last step of the epoch}
+    float s_zrefv[FAN_MAXSEG];                 // per run: increment of z_ref per row
+    int s_ra[FAN_MAXSEG], s_rb[FAN_MAXSEG], s_cls[FAN_MAXSEG], c_n[FAN_MAXSEG];
+    float rtab[36];                            // rcp(step) at the epoch's window boundaries (the crossing predicate)
+    unsigned queue[FAN_QCAP];
+    unsigned char lane_seg[32];
+    unsigned starts[FAN_MAXROWS / 32];         // bit r of word w: row 32w+r starts a run of equal n
+    int run_n[32];                             // n of the column's first 32 runs (more: recomputed on the fly)
 };
 
 // first row after `cur` that starts a new run (or nRows)
@@ -88,9 +74,8 @@ __device__ __forceinline__ int fan_next_start(const unsigned *starts, int cur, i
     }
 }
 
-// conservative range of real sample indices t with s + t*d inside [lo, hi)
-__device__ __forceinline__ void fan_slab(double s, double d, double lo, double hi, double &t0, double &t1,
-                                         bool &hit)
+// range of the chord parameter lambda in [0,1] with s + lambda*d inside [lo, hi)
+__device__ __forceinline__ void fan_slab(double s, double d, double lo, double hi, double &t0, double &t1, bool &hit)
 {
     if (d == 0.0) {
         hit = hit && (s >= lo && s < hi);
@@ -102,8 +87,6 @@ __device__ __forceinline__ void fan_slab(double s, double d, double lo, double h
     }
 }
 
-// predicated 16-byte read-only load: v keeps its value when `take` is false (no branch, so the load
-// can be issued a step ahead of its use)
 __device__ __forceinline__ void fan_ld4_if(float4 &v, const void *p, bool take)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -111,7 +94,13 @@ __device__ __forceinline__ void fan_ld4_if(float4 &v, const void *p, bool take)
                  : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
                  : "r"((int)take), "l"(p));
 }
-// packed fp32x2 (sm_100 FMUL2/FFMA2): one issue slot for two slices
+// base + (unsigned) byte offset in one instruction (IMAD.WIDE.U32)
+__device__ __forceinline__ const char *fan_at(const char *base, unsigned off)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"((unsigned long long)base));
+    return reinterpret_cast<const char *>(r);
+}
 __device__ __forceinline__ float2 fan_mul2(float w, float a, float b)
 {
     return __fmul2_rn(make_float2(w, w), make_float2(a, b));
@@ -120,357 +109,412 @@ __device__ __forceinline__ float2 fan_fma2(float w, float a, float b, float2 acc
 {
     return __ffma2_rn(make_float2(w, w), make_float2(a, b), acc);
 }
-__device__ __forceinline__ float2 fan_shfl_up2(float2 v, int d)
+
+// THE crossing predicate: first row that is above boundary k at the step whose reciprocal is r
+// (a = (k - sz) n / vz, b = dz0 / vz).  Every use goes through this function, bit for bit.
+__device__ __forceinline__ int fan_cv(float a, float r, float b)
 {
-    return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+    return __float2int_ru(__fmaf_rn(a, r, -b));            // F2I saturates: monotone for any finite input
+}
+__device__ __forceinline__ float fan_ak(int k, float szf, float nvz)
+{
+    return __fmul_rn(__fsub_rn((float)k, szf), nvz);
+}
+__device__ __forceinline__ float fan_rcp_step(int i)
+{
+    return i > 0 ? __frcp_rn((float)i) : 2.0f;             // decreasing in i, finite at the source
 }
 
-// inclusive running (P,Q) of chunk-local step i (i >= 0) at table columns c and c+1
-template <int LQ, int SB>
-__device__ __forceinline__ void fan_lookup(const float2 *T, const float2 *carry, int i, int c, float2 &lo,
-                                           float2 &hi)
+template <int CW, int NWARPS, int MINB, int MODE>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
 {
-    constexpr int TS = FanCfg<LQ, SB>::TS;
-    const int s = i >> FanCfg<LQ, SB>::LOGB;
-    const float2 *t = T + (i + s) * TS + c;
-    const float2 *k = carry + s * TS + c;
-    const float2 t0 = t[0], t1 = t[1], k0 = k[0], k1 = k[1];
-    lo = make_float2(t0.x + k0.x, t0.y + k0.y);
-    hi = make_float2(t1.x + k1.x, t1.y + k1.y);
-}
-
-// ---- phase 1 of a chunk: stream-local running sums of G, four slices per lane, into the table; then
-// the carries of the streams and the chunk totals.  kA = first slice of the window (multiple of 4),
-// nq = quads in it, nst = steps of the chunk.
-template <int LQ, int SB>
-__device__ __forceinline__ void fan_phase1(FanWarpSmem<LQ, SB> &sm, const float *__restrict__ vol, int sxs,
-                                           int sys, int kA, int nq, int nst, int lane)
-{
-    using Cfg = FanCfg<LQ, SB>;
-    constexpr int G = Cfg::G, CW = Cfg::CW, TS = Cfg::TS, B = SB;
-    const int g = lane / LQ, q = lane % LQ;                       // stream g, z quad q
-        const bool on = q < nq;
-        const float *__restrict__ base = vol + kA + 4 * q;
-        float2 pq0 = make_float2(0.f, 0.f), pq1 = pq0, pq2 = pq0, pq3 = pq0;   // running (P,Q) x 4 slices
-        float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
-        const int row0 = g * (B + 1);             // table row of the stream's first step
-        const float4 *wp = sm.w + row0;
-        float4 *Tw = reinterpret_cast<float4 *>(sm.T + row0 * TS + 4 * q);
-        float jf = (float)(g * B - CW / 2);
-        if (g * B < nst) {
-            // Two register sets of corner columns, one for the even and one for the odd steps: as soon
-            // as step s has consumed its set, the columns of step s+2 are requested into it (predicated:
-            // no load when the cell is the same), so a whole step of arithmetic covers the L2 latency
-            // and no register moves are needed.
-            // byte offsets are unsigned 32-bit (pax_ax_fan_launch checks the volume is < 4 GB):
-            // one 64-bit add per step, the other corners are uniform strides away
-            const char *bb = reinterpret_cast<const char *>(base);
-            const size_t dx4 = (size_t)sxs * 4, dy4 = (size_t)sys * 4;
-            // one register set: the columns of step s+1 are requested right after step s consumed them
-            float4 w = wp[0];
-            unsigned off = __float_as_uint(w.w);
-            {
-                const char *p00 = bb + off, *p10 = p00 + dy4;
-                fan_ld4_if(c00, p00, on); fan_ld4_if(c01, p00 + dx4, on);
-                fan_ld4_if(c10, p10, on); fan_ld4_if(c11, p10 + dx4, on);
-            }
-    #pragma unroll
-            for (int s = 0; s < B; ++s) {
-                float4 wn = w;
-                if (s + 1 < B) wn = wp[s + 1];
-                const unsigned offn = __float_as_uint(wn.w);
-                const bool chg = on && offn != off;
-                const float w11 = 1.f - w.x - w.y - w.z;              // the weights sum to one
-                const char *p00 = bb + offn, *p10 = p00 + dy4;
-                float2 v0 = fan_mul2(w.x, c00.x, c00.y), v1 = fan_mul2(w.x, c00.z, c00.w);
-                v0 = fan_fma2(w.y, c01.x, c01.y, v0); v1 = fan_fma2(w.y, c01.z, c01.w, v1);
-                v0 = fan_fma2(w.z, c10.x, c10.y, v0); v1 = fan_fma2(w.z, c10.z, c10.w, v1);
-                v0 = fan_fma2(w11, c11.x, c11.y, v0); v1 = fan_fma2(w11, c11.z, c11.w, v1);
-                if (s + 1 < B) {
-                    fan_ld4_if(c00, p00, chg); fan_ld4_if(c01, p00 + dx4, chg);
-                    fan_ld4_if(c10, p10, chg); fan_ld4_if(c11, p10 + dx4, chg);
-                }
-                pq0.x += v0.x; pq1.x += v0.y; pq2.x += v1.x; pq3.x += v1.y;
-                pq0.y = fmaf(jf, v0.x, pq0.y); pq1.y = fmaf(jf, v0.y, pq1.y);
-                pq2.y = fmaf(jf, v1.x, pq2.y); pq3.y = fmaf(jf, v1.y, pq3.y);
-                jf += 1.f;
-                if (on) {
-                    Tw[s * (TS / 2)] = make_float4(pq0.x, pq0.y, pq1.x, pq1.y);
-                    Tw[s * (TS / 2) + 1] = make_float4(pq2.x, pq2.y, pq3.x, pq3.y);
-                }
-                off = offn;
-                w = wn;
-            }
-        }
-        // carry of a stream = totals of the earlier streams: inclusive scan over g, minus own
-        float2 t0 = pq0, t1 = pq1, t2 = pq2, t3 = pq3;
-    #pragma unroll
-        for (int d = LQ; d < 32; d <<= 1) {
-            const float2 o0 = fan_shfl_up2(t0, d), o1 = fan_shfl_up2(t1, d);
-            const float2 o2 = fan_shfl_up2(t2, d), o3 = fan_shfl_up2(t3, d);
-            if (lane >= d) {
-                t0 = __fadd2_rn(t0, o0); t1 = __fadd2_rn(t1, o1);
-                t2 = __fadd2_rn(t2, o2); t3 = __fadd2_rn(t3, o3);
-            }
-        }
-        float4 *cw = reinterpret_cast<float4 *>(sm.carry + g * TS + 4 * q);
-        cw[0] = make_float4(t0.x - pq0.x, t0.y - pq0.y, t1.x - pq1.x, t1.y - pq1.y);
-        cw[1] = make_float4(t2.x - pq2.x, t2.y - pq2.y, t3.x - pq3.x, t3.y - pq3.y);
-        if (g == G - 1) {                           // inclusive total of the last stream = chunk total
-            float4 *tw = reinterpret_cast<float4 *>(sm.total + 4 * q);
-            tw[0] = make_float4(t0.x, t0.y, t1.x, t1.y);
-            tw[1] = make_float4(t2.x, t2.y, t3.x, t3.y);
-        }
-}
-
-// ---- phase 2 state of one detector row within a chunk
-struct FanRow {
-    float dzf, rinv, zc0, zl, kf, acc;
-    int j, hi;
-    bool up, bad;
-
-    // the row's own step range is re-derived in fp32 (the double version counted the samples; a boundary
-    // sample has zero weight, so an ulp either way is harmless)
-    __device__ __forceinline__ void init(int r, bool exists, double zr0, double zvr, double sz, float szf,
-                                         float kminf, float kmaxf, float fI0, float fI1, int c0, int nst)
-    {
-        const double ddz = zr0 + (double)r * zvr;
-        dzf = (float)ddz;
-        float flo = fI0, fhi = exists ? fI1 : -1.f;
-        const float rz = __frcp_rn(dzf);                      // inf when dzf == 0: not used then
-        if (dzf != 0.f) {
-            const float ta = (kminf - szf) * rz, tb = (kmaxf - szf) * rz;
-            flo = fmaxf(flo, ceilf(fminf(ta, tb)));
-            fhi = fminf(fhi, floorf(fmaxf(ta, tb)));
-        } else if (!(szf >= kminf && szf < kmaxf)) {
-            fhi = -1.f;
-        }
-        j = max((int)flo, c0) - c0;
-        hi = min((int)fhi, c0 + nst - 1) - c0;
-        if (j > hi) j = max(hi, -1) + 1;                      // nothing to do here: keep the look-up indices in range
-        rinv = fabsf(rz);
-        up = dzf > 0.f;
-        zc0 = (float)(sz + (double)c0 * ddz);
-        zl = fmaf((float)j, dzf, zc0);
-        // fp32 z may round onto the clip bounds: keep the slice pair inside [kmin, kmax] (tt then
-        // extrapolates by an ulp)
-        kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
-        acc = 0.f;
-        bad = false;
-    }
-
-    // one stretch (the steps from j on that stay in one slice pair), branch-free; a no-op once j > hi
-    template <int LQ, int SB>
-    __device__ __forceinline__ void stretch(const float2 *T, const float2 *carry, int kA, int nq, float kminf,
-                                            float kmaxf)
-    {
-        constexpr int W = FanCfg<LQ, SB>::W, CW = FanCfg<LQ, SB>::CW;
-        const bool live = j <= hi;
-        const float tt = zl - kf;
-        // steps that stay in slice pair (k, k+1): tt + m dz stays inside [0,1).  An exact hit of the boundary
-        // may go either way (the interpolant is continuous); dz == 0 gives inf or NaN here, which fminf turns
-        // into "the rest of the chunk".
-        const int ms = (int)fminf(floorf((up ? 1.f - tt : tt) * rinv), 1.0e4f);
-        const int je = max(min(hi, j + max(ms, 0)), 0);
-        const int kr = (int)kf - kA;
-        const int kk = min(max(kr, 0), W - 2);
-        bad |= live && (kr < 0 || kr > 4 * nq - 2);
-        float2 a0, a1, b0, b1;
-        fan_lookup<LQ, SB>(T, carry, max(j - 1, 0), kk, a0, a1);
-        fan_lookup<LQ, SB>(T, carry, je, kk, b0, b1);
-        if (j <= 0) { a0 = make_float2(0.f, 0.f); a1 = a0; }
-        const float dP0 = b0.x - a0.x, dQ0 = b0.y - a0.y;
-        const float dP1 = b1.x - a1.x, dQ1 = b1.y - a1.y;
-        const float alpha = fmaf((float)(CW / 2 - j), dzf, tt);                // t at index CW/2
-        const float val = fmaf(dzf, dQ1 - dQ0, fmaf(alpha, dP1 - dP0, dP0));
-        acc += live ? val : 0.f;
-        j = live ? je + 1 : j;
-        zl = fmaf((float)j, dzf, zc0);
-        kf = fminf(fmaxf(floorf(zl), kminf), kmaxf - 1.f);
-    }
-};
-
-template <int LQ, int SB, int NWARPS, int MODE>
-__global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
-{
-    using Cfg = FanCfg<LQ, SB>;
-    constexpr int W = Cfg::W, CW = Cfg::CW, LOGB = Cfg::LOGB;
-    static_assert(SB == 8 || SB == 16, "8 or 16 steps per stream");
     extern __shared__ __align__(16) unsigned char fan_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    FanWarpSmem<LQ, SB> &sm = reinterpret_cast<FanWarpSmem<LQ, SB> *>(fan_smem_raw)[warp];
+    const int rows_pad = (a.fan_rows + 3) & ~3;
+    const size_t per_warp = sizeof(FanSmem<CW>) + (size_t)rows_pad * sizeof(float);
+    FanSmem<CW> &sm = *reinterpret_cast<FanSmem<CW> *>(fan_smem_raw + (size_t)warp * per_warp);
+    float *rsum = reinterpret_cast<float *>(&sm + 1);             // running line integral of every row of the band
 
-    const int u = blockIdx.x * NWARPS + warp;
-    if (u >= a.nu) return;                                        // warps are independent: no barriers below
-    const int ia = blockIdx.y;
-    const int V0 = blockIdx.z * a.fan_rows;
+    // CTA order: angle fastest, then the column tile.  The angles of a launch are a few degrees apart, so at any
+    // time the resident CTAs walk chords through one narrow bow-tie of the volume, which stays in L2 while the
+    // bow-tie sweeps across (column-tile-fastest order re-read the volume from DRAM once per angle)
+    const int u = (blockIdx.x / a.fan_count) * NWARPS + warp;
+    if (u >= a.nu) return;                                        // warps are independent: no CTA barriers below
+    const int ia = blockIdx.x % a.fan_count;
+    const int V0 = blockIdx.y * a.fan_rows;
     const int nRows = min(a.fan_rows, a.nv - V0);
     const AngleDev &A = a.angles[a.first + ia];
     const double sx = A.sx, sy = A.sy, sz = A.sz;
-    const double zlo = (double)a.loz, zhi = (double)a.hiz;
     const int kmin = (int)a.loz, kmax = (int)a.hiz;               // slices a sample can touch: [kmin, kmax]
-    const float kminf = a.loz, kmaxf = a.hiz;
-    const int sxs = a.nzp, sys = a.nxp * a.nzp;
     const int xmaxc = (int)a.hix - 1, ymaxc = (int)a.hiy - 1;    // last in-plane cell whose +1 neighbour exists
     const float szf = (float)sz;
     const double dx = A.ox + u * A.ux - sx, dy = A.oy + u * A.uy - sy;
     const double dxy2 = dx * dx + dy * dy;
     const double racc = 1.0 / a.acc;
-    const double dz0 = A.oz + (double)V0 * A.vz - sz;             // P_z - S_z of the tile's row 0; +vz per row
-    unsigned my_ns = 0;
+    const double vz = A.vz;
+    const double dz0 = A.oz + (double)V0 * vz - sz;               // P_z - S_z of the band's row 0; +vz per row
+    const float bq = (float)(dz0 / vz);                           // the predicate's b
+    const double rvz = 1.0 / vz;
+    const int EP = a.fan_epoch;
+    const size_t dx4 = (size_t)a.nzp * 4, dy4 = (size_t)a.nxp * a.nzp * 4;
     float r2 = 0.f, mymax = -INFINITY;
-    bool bad = false;
+    unsigned my_ns = 0;
 
-    // ---- runs of rows with equal n = ceil(|P-S| / accuracy)  (TIGRE's lattice)
+    // ---- runs of rows with equal n (TIGRE's lattice); clear the rows' sums
+    int nlo = INT_MAX, nhi = 0;
     {
-        int last = -2;
+        int last = -2, nruns = 0;
         for (int r0 = 0; r0 < nRows; r0 += 32) {
             const bool in = r0 + lane < nRows;
-            const double dz = dz0 + (double)(r0 + lane) * A.vz;
+            const double dz = dz0 + (double)(r0 + lane) * vz;
             const int n = in ? (int)ceil(sqrt(dxy2 + dz * dz) * racc) : -1;
+            if (in) { nlo = min(nlo, n); nhi = max(nhi, n); rsum[r0 + lane] = 0.f; }
             int prev = __shfl_up_sync(0xffffffffu, n, 1);
             if (lane == 0) prev = last;
-            const unsigned m = __ballot_sync(0xffffffffu, in && n != prev);
+            const bool st = in && n != prev;
+            const unsigned m = __ballot_sync(0xffffffffu, st);
             if (lane == 0) sm.starts[r0 >> 5] = m;
+            const int ord = nruns + __popc(m & ((1u << lane) - 1u));
+            if (st && ord < 32) sm.run_n[ord] = n;
+            nruns += __popc(m);
             last = __shfl_sync(0xffffffffu, n, 31);
         }
+        nlo = __reduce_min_sync(0xffffffffu, nlo);
+        nhi = __reduce_max_sync(0xffffffffu, nhi);
         __syncwarp();
     }
 
-    int cur = 0;
-    while (cur < nRows) {
-        // ---- the run of rows [cur, e) that share n (uniform over the warp)
-        const int e = fan_next_start(sm.starts, cur, nRows);
-        const double dzc = dz0 + (double)cur * A.vz;
-        const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
-        const double rn = 1.0 / (double)nrun;
-        const double ddx = dx * rn, ddy = dy * rn;
-        double t0 = 0.0, t1 = (double)nrun;
-        bool hit = true;
-        fan_slab(sx, ddx, 0.0, (double)a.hix, t0, t1, hit);
-        fan_slab(sy, ddy, 0.0, (double)a.hiy, t0, t1, hit);
-        // ---- rows of the run: clear their sums, count their samples, find the run's step range
-        int I0 = INT_MAX, I1 = -1;
-        for (int r = cur + lane; r < e; r += 32) {
-            sm.rsum[r] = 0.f;
-            double tz0 = t0, tz1 = t1;
-            bool hz = hit;
-            fan_slab(sz, (dz0 + (double)r * A.vz) * rn, zlo, zhi, tz0, tz1, hz);
-            if (hz && tz0 <= tz1) {
-                const int i0 = (int)ceil(tz0), i1 = (int)floor(tz1);
-                if (i0 <= i1) { I0 = min(I0, i0); I1 = max(I1, i1); my_ns += (unsigned)(i1 - i0 + 1); }
-            }
-        }
-        I0 = __reduce_min_sync(0xffffffffu, I0);
-        I1 = __reduce_max_sync(0xffffffffu, I1);
-        if (I0 <= I1) {
-            // z (slices) of row r at step j:  sz + j * (zr0 + r * zvr)
-            const double zr0 = dz0 * rn, zvr = A.vz * rn;
-            const float fI0 = (float)I0, fI1 = (float)I1;
+    // ---- the chord's part inside the volume in x and y, as a range of lambda = i / n (all runs share it)
+    double lam0 = 0.0, lam1 = 1.0;
+    bool hit = true;
+    fan_slab(sx, dx, 0.0, (double)a.hix, lam0, lam1, hit);
+    fan_slab(sy, dy, 0.0, (double)a.hiy, lam0, lam1, hit);
+
+    if (hit && lam0 <= lam1) {
+        const int Emin = max((int)floor(lam0 * (double)nlo), 0), Emax = (int)ceil(lam1 * (double)nhi);
 #pragma unroll 1
-            for (int c0 = I0; c0 <= I1; c0 += CW) {
-                const int nst = min(CW, I1 - c0 + 1);             // steps of this chunk
-                __syncwarp();                                     // the previous chunk is done with w/off
-                // ---- phase 0, once per (run, chunk): in-plane cell and bilinear weights of every step.
-                // The chunk origin is split in double into an integer cell and a fraction; steps add t*d
-                // to the fraction in fp32 (|t| < CW): a position is good to ~2e-6 voxels, nothing accumulates.
+        for (int e0 = Emin; e0 <= Emax; e0 += EP) {
+            const int e1 = min(e0 + EP - 1, Emax);
+            const int ref = e0 + (EP >> 1);
+            const int nwin = (e1 - e0 + CW) / CW;
+            if (lane <= nwin) sm.rtab[lane] = fan_rcp_step(e0 + lane * CW);   // nwin <= 32 (pax_fan_configure)
+            int cur = 0, ri = 0;                                  // row, and the ordinal of the run it is in
+#pragma unroll 1
+            while (cur < nRows) {
+                // ================= pack runs (or pieces of runs) into the lanes of one pass (uniform over the warp)
+                int nseg = 0, ncls = 0, used = 0;
+#pragma unroll 1
+                while (cur < nRows && nseg < FAN_MAXSEG && used < 31) {
+                    const int e = fan_next_start(sm.starts, cur, nRows);
+                    int nrun;
+                    if (ri < 32) nrun = sm.run_n[ri];
+                    else {
+                        const double dzc = dz0 + (double)cur * vz;
+                        nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
+                    }
+                    const int I0 = max((int)ceil(lam0 * (double)nrun), 0), I1 = (int)floor(lam1 * (double)nrun);
+                    const int ja = max(I0, e0), jb = min(I1, e1);
+                    if (ja > jb) { cur = e; ++ri; continue; }     // the run has no sample in this epoch
+                    const double rn = 1.0 / (double)nrun;
+                    const float s0f = (float)(dz0 * rn), zvrf = (float)(vz * rn);
+                    const float fa = (float)ja, fb = (float)jb;
+                    const float sA = fmaf((float)cur, zvrf, s0f);
+                    const float zlo = szf + fminf(fa * sA, fb * sA);
+                    const int ka = max(kmin, (int)floorf(fmaxf(zlo - 4e-3f, -1.0e6f)));
+                    if (ka > kmax) { cur = nRows; break; }        // this row and all above it look over the volume
+                    const int qa = ka >> 2, avail = 32 - used;
+                    // last row whose highest slice (+1 neighbour) still falls into the lanes left
+                    const float lim = (float)(4 * (qa + avail) - 1) - 8e-3f - szf;
+                    float rmaxf = (float)(e - 1);
+                    if (zvrf > 0.f) {
+                        const float rz = __frcp_rn(zvrf);
+                        if (fb > 0.f) rmaxf = fminf(rmaxf, (__fdividef(lim, fb) - s0f) * rz - 2e-2f);
+                        if (fa > 0.f) rmaxf = fminf(rmaxf, (__fdividef(lim, fa) - s0f) * rz - 2e-2f);
+                    }
+                    int rb = min(max((int)floorf(fmaxf(rmaxf, -1.0f)) + 1, cur + 1), e);
+                    int nq;
+                    for (;;) {
+                        const float sB = fmaf((float)(rb - 1), zvrf, s0f);
+                        const float zhi = szf + fmaxf(fa * sB, fb * sB);
+                        const int kb = max(min(kmax, (int)floorf(fminf(zhi + 4e-3f, 1.0e6f)) + 1), ka);
+                        nq = (kb >> 2) - qa + 1;
+                        if (nq <= avail || rb <= cur + 1) break;
+                        --rb;
+                    }
+                    if (nq > avail) {
+                        if (used > 0) break;                      // start a new pass with this run
+                        if (lane == 0 && a.fault) atomicExch(a.fault, 1);   // a single row does not fit: see pax_fan_configure
+                        nq = avail;
+                    }
+                    // the run's lattice: runs with the same n (below and above the source plane) share their steps
+                    int cls = 0;
+                    while (cls < ncls && sm.c_n[cls] != nrun) ++cls;
+                    if (lane == 0) {
+                        const int g = nseg;
+                        sm.s_ra[g] = cur; sm.s_rb[g] = rb; sm.s_cls[g] = cls;
+                        sm.s_i[g] = make_int4(used, nq, qa, jb);
+                        sm.s_f[g] = make_float4((float)((double)nrun * rvz), s0f, zvrf, (float)(sz + (double)ref * dz0 * rn));
+                        sm.s_zrefv[g] = (float)((double)ref * vz * rn);
+                        if (cls == ncls) {
+                            // in-plane origin of the epoch, split in double into an integer cell and a fraction; steps
+                            // add t*d to the fraction in fp32 (t < EP): a position is good to a few 1e-6 voxels
+                            const double ddx = dx * rn, ddy = dy * rn;
+                            const double ex = sx + (double)e0 * ddx, ey = sy + (double)e0 * ddy;
+                            const double exi = floor(ex), eyi = floor(ey);
+                            sm.c_n[cls] = nrun;
+                            sm.c_geo[cls] = make_float4((float)ddx, (float)ddy, (float)(ex - exi), (float)(ey - eyi));
+                            sm.c_cell[cls] = make_int4((int)exi, (int)eyi, ja, jb);
+                        }
+                    }
+                    __syncwarp();
+                    if (cls == ncls) ++ncls;
+                    used += nq;
+                    ++nseg;
+                    cur = rb;
+                    if (rb == e) ++ri;
+                }
+                if (nseg == 0) continue;
+
+                // ================= the pass
+                int myseg = -1;
+#pragma unroll 1
+                for (int g = 0; g < nseg; ++g) {
+                    const int4 si = sm.s_i[g];
+                    if (lane >= si.x && lane < si.x + si.y) myseg = g;
+                }
+                const bool on = myseg >= 0;
+                const int sg = on ? myseg : 0;
+                const int4 mysi = sm.s_i[sg];
+                const int quad = mysi.z + lane - mysi.x;
+                const int segra = sm.s_ra[sg], segrb = sm.s_rb[sg];
+                const int segjb = mysi.w;                         // last step of my run in this epoch: no sample, hence
+                                                                  // no crossing to serve, after it
+                sm.lane_seg[lane] = (unsigned char)sg;
+                float ak0, ak1, ak2, ak3;
                 {
-                    const double ex = sx + (double)c0 * ddx, ey = sy + (double)c0 * ddy;
-                    const double exi = floor(ex), eyi = floor(ey);
-                    const float exf = (float)(ex - exi), eyf = (float)(ey - eyi);
-                    const int exc = (int)exi, eyc = (int)eyi;
-                    const float fddx = (float)ddx, fddy = (float)ddy;
-#pragma unroll
-                    for (int t = lane; t < CW; t += 32) {
-                        // a step past the run's end reads the all-zero rim column (0,0) with weight one
+                    const float nvz = sm.s_f[sg].x;
+                    ak0 = fan_ak(4 * quad + 0, szf, nvz); ak1 = fan_ak(4 * quad + 1, szf, nvz);
+                    ak2 = fan_ak(4 * quad + 2, szf, nvz); ak3 = fan_ak(4 * quad + 3, szf, nvz);
+                }
+                int cs0, cs1, cs2, cs3;                           // rows above my boundaries so far: [cs, segrb)
+                {
+                    const float r0 = sm.rtab[0];
+                    cs0 = min(max(fan_cv(ak0, r0, bq), segra), segrb); cs1 = min(max(fan_cv(ak1, r0, bq), segra), segrb);
+                    cs2 = min(max(fan_cv(ak2, r0, bq), segra), segrb); cs3 = min(max(fan_cv(ak3, r0, bq), segra), segrb);
+                }
+                // the four corner columns of in-plane cell (0,0), at my quad
+                const char *b00 = reinterpret_cast<const char *>(a.vol0 + 4 * (on ? quad : 0));
+                const char *b01 = b00 + dx4, *b10 = b00 + dy4, *b11 = b10 + dx4;
+                const float4 *wp = sm.w[sm.s_cls[sg]];
+                float *const ring = sm.ring + 4;
+                float4 Aq = make_float4(0.f, 0.f, 0.f, 0.f), Cq = Aq;     // running (A, C) of my four slices
+                float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
+                // event words of my four slices: row | slot << 16 | edge flags (no neighbour slice below / above
+                // inside the run's lanes: it is a zero slice) | direction
+                const unsigned evw = ((unsigned)(lane * 4) << 16);
+                const unsigned elo = (lane == mysi.x) ? (1u << 23) : 0u, ehi = (lane == mysi.x + mysi.y - 1) ? (1u << 24) : 0u;
+
+                // weights and cells of `count` steps from `first` on into slots slot0.., all lattices of the pass
+                auto fill_w = [&](int first, int count, int slot0) {
+                    for (int q = lane; q < ncls * count; q += 32) {
+                        const int g = q / count, t = q - g * count, i = first + t;
+                        const int4 cc = sm.c_cell[g];
+                        // a step outside the run's range reads the all-zero rim column (0,0) with weight one
                         float4 w = make_float4(1.f, 0.f, 0.f, __uint_as_float(0u));
-                        if (t < nst) {
-                            const float px = fmaf((float)t, fddx, exf), py = fmaf((float)t, fddy, eyf);
-                            const float flx = floorf(px), fly = floorf(py);
-                            const int cx = min(max(exc + (int)flx, 0), xmaxc);
-                            const int cy = min(max(eyc + (int)fly, 0), ymaxc);
-                            // fraction against the CLAMPED cell: a sample the double clip admitted may sit
-                            // an ulp outside in fp32, and must then weigh the rim, not the next column
-                            const float fx = fminf(fmaxf(px - (float)(cx - exc), 0.f), 1.f);
-                            const float fy = fminf(fmaxf(py - (float)(cy - eyc), 0.f), 1.f);
+                        if (i >= cc.z && i <= cc.w) {
+                            const float4 cg = sm.c_geo[g];
+                            const float tf = (float)(i - e0);
+                            const float px = fmaf(tf, cg.x, cg.z), py = fmaf(tf, cg.y, cg.w);
+                            const int ix = __float2int_rd(px), iy = __float2int_rd(py);
+                            const int cx = min(max(cc.x + ix, 0), xmaxc);
+                            const int cy = min(max(cc.y + iy, 0), ymaxc);
+                            // fraction against the CLAMPED cell: a sample the double clip admitted may sit an ulp
+                            // outside in fp32, and must then weigh the rim, not the next column
+                            const float fx = fminf(fmaxf(px - (float)(cx - cc.x), 0.f), 1.f);
+                            const float fy = fminf(fmaxf(py - (float)(cy - cc.y), 0.f), 1.f);
                             const unsigned off = (unsigned)((cy * a.nxp + cx) * a.nzp) * 4u;
                             const float gx = 1.f - fx, gy = 1.f - fy;
                             w = make_float4(gx * gy, fx * gy, gx * fy, __uint_as_float(off));
                         }
-                        sm.w[t + (t >> LOGB)] = w;
+                        sm.w[g][slot0 + t] = w;
+                    }
+                };
+                fill_w(e0, 1, CW);
+                fill_w(e0 + 1, CW, 0);
+                __syncwarp();
+                float4 wv = wp[CW];
+                unsigned off = __float_as_uint(wv.w);
+                fan_ld4_if(c00, fan_at(b00, off), on); fan_ld4_if(c01, fan_at(b01, off), on);
+                fan_ld4_if(c10, fan_at(b10, off), on); fan_ld4_if(c11, fan_at(b11, off), on);
+                float jf = (float)(e0 - ref);
+#pragma unroll 1
+                for (int m = 0; m < nwin; ++m) {
+                    const int w0 = e0 + m * CW;
+                    if (m) { fill_w(w0 + 1, CW, 0); __syncwarp(); }
+                    // ---- CW steps: running (A, C) of my four slices into the ring
+                    const int iend = min(w0 + CW, e1);
+                    int lo0 = 0, lo1 = 0, lo2 = 0, lo3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0, mine = 0, incl = 0;
+                    unsigned up = 0;
+#pragma unroll
+                    for (int t = 0; t < CW; ++t) {
+                        const float4 wn = wp[t];                   // the next step
+                        const unsigned offn = __float_as_uint(wn.w);
+                        const bool chg = on && offn != off;
+                        const float w11 = 1.f - wv.x - wv.y - wv.z;              // the weights sum to one
+                        float2 v0 = fan_mul2(wv.x, c00.x, c00.y), v1 = fan_mul2(wv.x, c00.z, c00.w);
+                        v0 = fan_fma2(wv.y, c01.x, c01.y, v0); v1 = fan_fma2(wv.y, c01.z, c01.w, v1);
+                        v0 = fan_fma2(wv.z, c10.x, c10.y, v0); v1 = fan_fma2(wv.z, c10.z, c10.w, v1);
+                        v0 = fan_fma2(w11, c11.x, c11.y, v0); v1 = fan_fma2(w11, c11.z, c11.w, v1);
+                        // the columns of the next step, as soon as this one has consumed the registers
+                        fan_ld4_if(c00, fan_at(b00, offn), chg); fan_ld4_if(c01, fan_at(b01, offn), chg);
+                        fan_ld4_if(c10, fan_at(b10, offn), chg); fan_ld4_if(c11, fan_at(b11, offn), chg);
+                        // (scalar accumulates: packed ones would pin the sums to register pairs that the 16-byte
+                        // stores then have to gather with eight moves)
+                        Aq.x += v0.x; Aq.y += v0.y; Aq.z += v1.x; Aq.w += v1.y;
+                        Cq.x = fmaf(jf, v0.x, Cq.x); Cq.y = fmaf(jf, v0.y, Cq.y);
+                        Cq.z = fmaf(jf, v1.x, Cq.z); Cq.w = fmaf(jf, v1.y, Cq.w);
+                        jf += 1.f;
+                        // (idle lanes store too: predicating the stores measured 4 % slower)
+                        *reinterpret_cast<float4 *>(ring + t * 256 + 4 * lane) = Aq;
+                        *reinterpret_cast<float4 *>(ring + t * 256 + 128 + 4 * lane) = Cq;
+                        off = offn;
+                        wv = wn;
+                    }
+                    __syncwarp();
+                    // ---- crossings at steps w0+1 .. iend (prefix through the step before, i.e. ring row t-1)
+                    {
+                        const int il = min(iend, segjb);
+                        int c0 = cs0, c1 = cs1, c2 = cs2, c3 = cs3;
+                        if (on && il > w0) {
+                            // (the predicate's reciprocal: tabulated at the window boundaries, else -- the run's
+                            // last window -- computed by the same function)
+                            const float re = (il == w0 + CW) ? sm.rtab[m + 1] : fan_rcp_step(il);
+                            c0 = min(max(fan_cv(ak0, re, bq), segra), segrb); c1 = min(max(fan_cv(ak1, re, bq), segra), segrb);
+                            c2 = min(max(fan_cv(ak2, re, bq), segra), segrb); c3 = min(max(fan_cv(ak3, re, bq), segra), segrb);
+                        }
+                        lo0 = min(c0, cs0); n0 = abs(c0 - cs0); up |= (c0 < cs0) ? 0x80000000u : 0u;
+                        lo1 = min(c1, cs1); n1 = abs(c1 - cs1); up |= (c1 < cs1) ? 0x40000000u : 0u;
+                        lo2 = min(c2, cs2); n2 = abs(c2 - cs2); up |= (c2 < cs2) ? 0x20000000u : 0u;
+                        lo3 = min(c3, cs3); n3 = abs(c3 - cs3); up |= (c3 < cs3) ? 0x10000000u : 0u;
+                        cs0 = c0; cs1 = c1; cs2 = c2; cs3 = c3;
+                        mine = n0 + n1 + n2 + n3;
+                        incl = mine;
+                    }
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll 1
+                    for (int qb = 0; qb < total; qb += FAN_QCAP) {
+                        // my events into the queue
+                        {
+                            const int i0 = incl - mine - qb, i1 = i0 + n0, i2 = i1 + n1, i3 = i2 + n2;
+                            const unsigned e0w = (unsigned)lo0 | evw | elo | (up & 0x80000000u);
+                            const unsigned e1w = (unsigned)lo1 | (evw + (1u << 16)) | ((up << 1) & 0x80000000u);
+                            const unsigned e2w = (unsigned)lo2 | (evw + (2u << 16)) | ((up << 2) & 0x80000000u);
+                            const unsigned e3w = (unsigned)lo3 | (evw + (3u << 16)) | ehi | ((up << 3) & 0x80000000u);
+                            const int nmax = max(max(n0, n1), max(n2, n3));
+                            for (int r = 0; r < nmax; ++r) {
+                                if (r < n0 && (unsigned)(i0 + r) < FAN_QCAP) sm.queue[i0 + r] = e0w + r;
+                                if (r < n1 && (unsigned)(i1 + r) < FAN_QCAP) sm.queue[i1 + r] = e1w + r;
+                                if (r < n2 && (unsigned)(i2 + r) < FAN_QCAP) sm.queue[i2 + r] = e2w + r;
+                                if (r < n3 && (unsigned)(i3 + r) < FAN_QCAP) sm.queue[i3 + r] = e3w + r;
+                            }
+                        }
+                        __syncwarp();
+                        const int nev = min(FAN_QCAP, total - qb);
+                        for (int q = lane; q < nev; q += 32) {
+                            const unsigned ev = sm.queue[q];
+                            const int v = (int)(ev & 0xffffu), slot = (int)((ev >> 16) & 0x7fu);
+                            const int g = sm.lane_seg[slot >> 2];
+                            const int4 si = sm.s_i[g];
+                            const float4 sf = sm.s_f[g];
+                            const float fk = (float)(4 * (si.z - si.x) + slot), fv = (float)v;
+                            const float ak = __fmul_rn(__fsub_rn(fk, szf), sf.x);
+                            // first step of the window at which the row is on the new side of the boundary.  The
+                            // closed form may differ from the predicate's by a step when z hits the boundary to
+                            // ~1e-5: harmless, the interpolant is continuous there (only WHICH window serves the
+                            // crossing has to agree with the pair found at the epoch's end, and that is the predicate's)
+                            const int th = min(iend, si.w) - w0;
+                            const int tl = min(max(__float2int_ru(__fdividef(ak, fv + bq)) - w0, 1), th);
+                            const float *row = ring + (tl - 1) * 256 + slot;
+                            float am = row[-1], a0_ = row[0], ap = row[1], cm = row[127], c0_ = row[128], cp = row[129];
+                            if (ev & (1u << 23)) { am = 0.f; cm = 0.f; }
+                            if (ev & (1u << 24)) { ap = 0.f; cp = 0.f; }
+                            const float d2a = fmaf(-2.f, a0_, am + ap), d2c = fmaf(-2.f, c0_, cm + cp);
+                            const float sv = fmaf(fv, sf.z, sf.y);
+                            const float tau = fmaf(fv, sm.s_zrefv[g], sf.w) - fk;
+                            const float val = fmaf(tau, d2a, sv * d2c);
+                            atomicAdd(rsum + v, (int)ev < 0 ? -val : val);
+                        }
+                        __syncwarp();
                     }
                 }
-                // z of row r at the first / last step of the chunk: Aa + Ba r, Ab + Bb r  (Ba, Bb >= 0)
-                const double ja = (double)c0, jb = (double)(c0 + nst - 1);
-                const float Aa = (float)(sz + ja * zr0), Ba = (float)(ja * zvr);
-                const float Ab = (float)(sz + jb * zr0), Bb = (float)(jb * zvr);
-                // (approximate reciprocals: the row bounds below are re-checked against the window)
-                const float rBa = Ba > 0.f ? __frcp_rn(Ba) : 0.f, rBb = Bb > 0.f ? __frcp_rn(Bb) : 0.f;
-                // rows that can touch a slice during this chunk
-                int ga = cur, ge = e;
+                // ---- end of the epoch: every row reads its slice pair once
                 {
-                    const float lo_a = Ba > 0.f ? (kminf - 1.f - Aa) * rBa : (Aa >= kminf - 1.f ? -1e9f : 1e9f);
-                    const float lo_b = Bb > 0.f ? (kminf - 1.f - Ab) * rBb : (Ab >= kminf - 1.f ? -1e9f : 1e9f);
-                    const float hi_a = Ba > 0.f ? (kmaxf + 1.f - Aa) * rBa : (Aa <= kmaxf + 1.f ? 1e9f : -1e9f);
-                    const float hi_b = Bb > 0.f ? (kmaxf + 1.f - Ab) * rBb : (Ab <= kmaxf + 1.f ? 1e9f : -1e9f);
-                    ga = max(ga, (int)fmaxf(fminf(ceilf(fminf(lo_a, lo_b)), 1e6f), -1e6f));
-                    ge = min(ge, (int)fmaxf(fminf(floorf(fmaxf(hi_a, hi_b)), 1e6f), -1e6f) + 1);
+                    const float *row = ring + (e1 - (e0 + (nwin - 1) * CW)) * 256;
+#pragma unroll 1
+                    for (int g = 0; g < nseg; ++g) {
+                        const int4 si = sm.s_i[g];
+                        const float4 sf = sm.s_f[g];
+                        const float zrv = sm.s_zrefv[g];
+                        // the run's last step of the epoch; the sums do not change after it (G = 0)
+                        const float re = fan_rcp_step(si.w), fe = (float)si.w;
+                        const int k0 = 4 * si.z;
+                        for (int v = sm.s_ra[g] + lane; v < sm.s_rb[g]; v += 32) {
+                            const float fv = (float)v;
+                            const float sv = fmaf(fv, sf.z, sf.y);
+                            int K = __float2int_rd(fmaf(fe, sv, szf));
+                            // the pair the PREDICATE puts the row in (an ulp of z may disagree with it)
+                            if (v >= fan_cv(fan_ak(K + 1, szf, sf.x), re, bq)) ++K;
+                            else if (v < fan_cv(fan_ak(K, szf, sf.x), re, bq)) --K;
+                            const int kap = K - k0;
+                            if (kap >= 0 && kap + 1 < 4 * si.y) {
+                                const float *pr = row + 4 * si.x + kap;
+                                const float aK = pr[0], aK1 = pr[1], cK = pr[128], cK1 = pr[129];
+                                const float tau = fmaf(fv, zrv, sf.w) - (float)K;
+                                rsum[v] += fmaf(sv, cK1 - cK, fmaf(tau, aK1 - aK, aK));
+                            }
+                        }
+                    }
                 }
                 __syncwarp();
-                // ---- groups of rows whose z window over this chunk fits the W slices of a stream
-#pragma unroll 1
-                while (ga < ge) {
-                    const float fga = (float)ga;
-                    const float zmin = fminf(fmaf(Ba, fga, Aa), fmaf(Bb, fga, Ab));
-                    const int kA = max(kmin, (int)floorf(zmin - 2e-3f)) & ~3;
-                    int gb = min(ge, ga + a.fan_piece);
-                    if (kA + W - 1 < kmax) {
-                        // floor(zmax + eps) + 1 <= kA + W - 1  for both ends of the chunk
-                        const float lim = (float)(kA + W - 1) - 4e-3f;
-                        const float ra = Ba > 0.f ? (lim - Aa) * rBa : 1e9f, rb = Bb > 0.f ? (lim - Ab) * rBb : 1e9f;
-                        gb = min(gb, (int)fmaxf(fminf(floorf(fminf(ra, rb) - 1e-2f), 1e6f), -1e6f) + 1);
-                    }
-                    if (gb <= ga) {                               // a single row does not fit: see pax_fan_configure
-                        if (lane == 0 && a.fault) atomicExch(a.fault, 1);
-                        gb = ga + 1;
-                    }
-                    const float fgl = (float)(gb - 1);
-                    const float zmax = fmaxf(fmaf(Ba, fgl, Aa), fmaf(Bb, fgl, Ab));
-                    const int kB = min(kmax, (int)floorf(zmax + 2e-3f) + 1);
-                    const int nq = (kB - kA + 4) >> 2;            // quads in the window
-                    if (nq > LQ && lane == 0 && a.fault) atomicExch(a.fault, 3);
-                    if (nq > 0) {
-                        fan_phase1<LQ, SB>(sm, a.vol0, sxs, sys, kA, nq, nst, lane);
-                        __syncwarp();
-                        // ---- phase 2: two detector rows per lane and pass, advanced side by side so that their
-                        // (serial) address and look-up chains overlap
-                        for (int r = ga + lane; r < gb; r += 64) {
-                            FanRow ra, rb;
-                            ra.init(r, true, zr0, zvr, sz, szf, kminf, kmaxf, fI0, fI1, c0, nst);
-                            rb.init(r + 32, r + 32 < gb, zr0, zvr, sz, szf, kminf, kmaxf, fI0, fI1, c0, nst);
-                            while (ra.j <= ra.hi || rb.j <= rb.hi) {
-                                ra.template stretch<LQ, SB>(sm.T, sm.carry, kA, nq, kminf, kmaxf);
-                                rb.template stretch<LQ, SB>(sm.T, sm.carry, kA, nq, kminf, kmaxf);
-                            }
-                            bad |= ra.bad | rb.bad;
-                            sm.rsum[r] += ra.acc;
-                            if (r + 32 < gb) sm.rsum[r + 32] += rb.acc;
-                        }
-                        if (bad && a.fault) atomicExch(a.fault, 2);        // cannot happen: the group was cut to fit
-                        __syncwarp();                             // the table is free for the next group
-                    }
-                    ga = gb;
-                }
             }
         }
-        __syncwarp();
-        // ---- epilogue of the run.  The warps of the CTA own adjacent columns and fill one 32-byte sector
-        // of every row between them; L2 merges the partial writes.
+    }
+    __syncwarp();
+
+    // ---- epilogue, run by run (the step length in mm depends on n).  The warps of the CTA own adjacent columns and
+    // fill one 32-byte sector of every row between them; L2 merges the partial writes.
+    int cur = 0;
+    while (cur < nRows) {
+        const int e = fan_next_start(sm.starts, cur, nRows);
+        const double dzc = dz0 + (double)cur * vz;
+        const int nrun = (int)ceil(sqrt(dxy2 + dzc * dzc) * racc);
+        const double rn = 1.0 / (double)nrun;
+        const double ddx = dx * rn, ddy = dy * rn;
+        double t0 = 0.0, t1 = (double)nrun;
+        bool hitr = true;
+        if (a.nsamples) {
+            fan_slab(sx, ddx, 0.0, (double)a.hix, t0, t1, hitr);
+            fan_slab(sy, ddy, 0.0, (double)a.hiy, t0, t1, hitr);
+        }
         for (int r = cur + lane; r < e; r += 32) {
             const int v = V0 + r;
             const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
-            const double mx = ddx * a.dX, my = ddy * a.dY, mz = (dz0 + (double)r * A.vz) * rn * a.dZ;
-            const float p0 = sm.rsum[r] * (float)sqrt(mx * mx + my * my + mz * mz);
+            const double mx = ddx * a.dX, my = ddy * a.dY, mz = (dz0 + (double)r * vz) * rn * a.dZ;
+            const float p0 = rsum[r] * (float)sqrt(mx * mx + my * my + mz * mz);
+            if (a.nsamples) {                                     // exact count of the samples inside the open box
+                double tz0 = t0, tz1 = t1;
+                bool hz = hitr;
+                fan_slab(sz, (dz0 + (double)r * vz) * rn, (double)a.loz, (double)a.hiz, tz0, tz1, hz);
+                if (hz && tz0 <= tz1) {
+                    const int i0 = (int)ceil(tz0), i1 = (int)floor(tz1);
+                    if (i0 <= i1) my_ns += (unsigned)(i1 - i0 + 1);
+                }
+            }
             if (MODE == PAX_AX_PLAIN) {
                 float val = a.a0 * p0;
                 if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
@@ -505,54 +549,93 @@ __global__ void __launch_bounds__(NWARPS * 32) k_ax_fan(const AxArgs a)
 }
 
 // ------------------------------------------------------------------------------ host side
-// Piece size (rows) for which every chunk's z window fits the lanes, per kernel configuration, and
-// the mean length of the equal-n runs (what the sharing is worth).  All from the plan's geometry.
-template <int LQ, int SB>
-static int fan_piece_rows(const PaxGeo &g, double vz, double tau, double slope)
+template <int CW, int NWARPS, int MINB, int MODE>
+static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
 {
-    // window of a chunk <= rows*vz*tau (spread of the rows) + steps*slope (travel) + 2 (floor, +1)
-    //                      + 3 (alignment to a quad) + slack  must fit W slices
-    const double room = (double)FanCfg<LQ, SB>::W - 5.3 - FanCfg<LQ, SB>::CW * slope;
-    int rows = room > 0 ? (int)std::floor(room / (vz * tau)) : 0;
-    rows = std::max(0, std::min(rows, std::min(FAN_GROUP, (int)g.nDetecV)));
-    return rows >= 32 ? rows / 32 * 32 : rows;      // whole warps of rows: no idle lanes in phase 2
+    const size_t per_warp = sizeof(FanSmem<CW>) + (size_t)((a.fan_rows + 3) & ~3) * sizeof(float);
+    const size_t smem = per_warp * NWARPS;
+    PAX_REQUIRE(smem <= 227 * 1024, "pax_ax: fan-plane tables do not fit shared memory");
+    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<CW, NWARPS, MINB, MODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AxArgs b = a;
+    b.fan_count = count;
+    dim3 grid(pax_cdiv(a.nu, NWARPS) * count, pax_cdiv(a.nv, a.fan_rows));
+    k_ax_fan<CW, NWARPS, MINB, MODE><<<grid, NWARPS * 32, smem, st>>>(b);
+    return PAX_OK;
 }
 
-#define FAN_NW8 5            // W=32 tables are twice as large: five warps per CTA, two CTAs per SM
+template <int CW, int NWARPS, int MINB>
+static int fan_launch_mode(const AxArgs &a, int mode, int count, cudaStream_t st)
+{
+    return mode == PAX_AX_PLAIN ? fan_launch<CW, NWARPS, MINB, PAX_AX_PLAIN>(a, count, st)
+                                : fan_launch<CW, NWARPS, MINB, PAX_AX_RESIDUAL>(a, count, st);
+}
 
+int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, cudaStream_t st)
+{
+    AxArgs a = a0;
+    a.fan_rows = p->fan_rows;
+    a.fan_epoch = p->fan_epoch;
+    a.fault = p->d_fault;
+    PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
+    PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
+    PAX_REQUIRE(p->fan_epoch >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
+                                   "(the z travel of a single detector row exceeds its lanes)");
+    switch (p->fan_cw * 10000 + p->fan_warps * 100 + p->fan_minb) {
+    case 80404: return fan_launch_mode<8, 4, 4>(a, mode, count, st);          // the default
+    case 80802: return fan_launch_mode<8, 8, 2>(a, mode, count, st);
+    case 40404: return fan_launch_mode<4, 4, 4>(a, mode, count, st);
+    default: break;
+    }
+    return pax_set_error(PAX_ERR_INVALID, "pax_ax: unsupported fan configuration CW=%d warps=%d minb=%d", p->fan_cw,
+                         p->fan_warps, p->fan_minb);
+}
+
+// Epoch length, rows per warp and launch shape from the plan's geometry.
 int pax_fan_configure(PaxPlan *p)
 {
     const PaxGeo &g = p->geo;
-    const double vz = g.dDetecV / g.dVoxelZ;
     const double dmax = std::fmax(g.dVoxelX, g.dVoxelY);
-    const double hx = 0.5 * g.nVoxelX * g.dVoxelX, hy = 0.5 * g.nVoxelY * g.dVoxelY;
-    // tau: largest fraction of a ray's length at which it can still be inside the volume (far corner);
-    // slope: largest |dz| per step of any ray, in slices
-    double tau = 0.0, slope = 0.0;
+    // largest |dz| per step of any ray, in slices
+    double slope = 0.0;
     for (const AngleDev &A : p->h_angles) {
-        const double rx = hx + std::fabs(A.offOX) + g.dVoxelX, ry = hy + std::fabs(A.offOY) + g.dVoxelY;
-        tau = std::fmax(tau, std::fmin(1.0, ((double)A.DSO + std::sqrt(rx * rx + ry * ry)) / (double)A.DSD));
         const double nmin = std::ceil((double)A.DSD / dmax / g.accuracy);
         const double za = std::fabs(A.oz - A.sz), zb = std::fabs(A.oz + (g.nDetecV - 1) * A.vz - A.sz);
         slope = std::fmax(slope, std::fmax(za, zb) / nmin);
     }
-    const int p4 = fan_piece_rows<4, 8>(g, vz, tau, slope);
-    const int p8 = fan_piece_rows<8, 16>(g, vz, tau, slope);
-    // a W=32 chunk costs twice a W=16 chunk per step: take it when it carries more than twice the rows
-    const char *force = getenv("PAX_FAN_LQ");                  // tuning hook
-    int lq = (p8 > 3 * p4) ? 8 : 4;                             // (measured at C2: 12.1 ms vs 10.0 ms)
-    if (force && (atoi(force) == 4 || atoi(force) == 8)) lq = atoi(force);
-    p->fan_lq = lq;
-    // worst-case number of rows whose z window fits (AUTO's criterion, pax_plan_fan_info); the kernel
-    // itself cuts the groups per chunk from the actual z range, up to FAN_GROUP rows
-    p->fan_fit = lq == 8 ? p8 : p4;
-    p->fan_piece = p->fan_fit >= 1 ? FAN_GROUP : 0;
-    p->fan_warps = lq == 8 ? FAN_NW8 : FAN_NW;
-    // rows one warp walks: whole columns when short, else equal tiles of <= FAN_MAXTILE rows
-    const int tiles = (g.nDetecV + FAN_MAXTILE - 1) / FAN_MAXTILE;
+    const char *e;
+    int cw = 8, nw = 4;
+    if ((e = getenv("PAX_FAN_CW")) && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16)) cw = atoi(e);   // tuning hooks
+    if ((e = getenv("PAX_FAN_NW")) && (atoi(e) == 4 || atoi(e) == 8)) nw = atoi(e);
+    int minb = 16 / nw;
+    if ((e = getenv("PAX_FAN_MINB")) && atoi(e) >= 1) minb = atoi(e);
+    p->fan_minb = minb;
+    // a single row must fit the 32 lanes (128 slices) of a pass over one epoch, with room to spare for its
+    // neighbours: halve the epoch until its z travel is at most 64 slices
+    int ep = 128;
+    if ((e = getenv("PAX_FAN_EPOCH")) && atoi(e) >= cw && atoi(e) <= FAN_EPMAX) ep = atoi(e) / cw * cw;
+    if (ep > 32 * cw) ep = 32 * cw;                             // at most 32 windows per epoch (rtab)
+    while (ep >= cw && ep * slope > 64.0) ep /= 2;
+    if (ep < cw) ep = 0;
+    else ep = ep / cw * cw;
+    p->fan_epoch = ep;
+    p->fan_cw = cw;
+    p->fan_warps = nw;
+    const int tiles = (g.nDetecV + FAN_MAXROWS - 1) / FAN_MAXROWS;
     p->fan_rows = (g.nDetecV + tiles - 1) / tiles;
-    // mean run length of equal n over three columns of the first angle
+    // AUTO's criteria (pax_plan_projector, pax_plan_fan_info): how many detector rows fit the 32 lanes of a warp
+    // over one epoch in the worst case, and how long the runs of equal n are (what the sharing is worth)
     {
+        const double vz = g.dDetecV / g.dVoxelZ;
+        const double hx = 0.5 * g.nVoxelX * g.dVoxelX, hy = 0.5 * g.nVoxelY * g.dVoxelY;
+        double tau = 0.0;       // largest fraction of a ray's length at which it can still be inside the volume
+        for (const AngleDev &A : p->h_angles) {
+            const double rx = hx + std::fabs(A.offOX) + g.dVoxelX, ry = hy + std::fabs(A.offOY) + g.dVoxelY;
+            tau = std::fmax(tau, std::fmin(1.0, ((double)A.DSO + std::sqrt(rx * rx + ry * ry)) / (double)A.DSD));
+        }
+        const double room = 128.0 - 6.0 - ep * slope;
+        int fit = (ep > 0 && room > 0) ? (int)std::floor(room / (vz * tau)) : 0;
+        p->fan_fit = std::max(ep > 0 ? 1 : 0, std::min(fit, (int)g.nDetecV));
         const AngleDev &A = p->h_angles[0];
         long runs = 0;
         const int us[3] = {0, g.nDetecU / 2, g.nDetecU - 1};
@@ -569,33 +652,4 @@ int pax_fan_configure(PaxPlan *p)
         p->fan_run = 3.0 * g.nDetecV / (double)runs;
     }
     return PAX_OK;
-}
-
-template <int LQ, int SB, int NWARPS, int MODE>
-static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
-{
-    const size_t smem = sizeof(FanWarpSmem<LQ, SB>) * NWARPS;
-    PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan<LQ, SB, NWARPS, MODE>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(pax_cdiv(a.nu, NWARPS), count, pax_cdiv(a.nv, a.fan_rows));
-    k_ax_fan<LQ, SB, NWARPS, MODE><<<grid, NWARPS * 32, smem, st>>>(a);
-    return PAX_OK;
-}
-
-int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, cudaStream_t st)
-{
-    AxArgs a = a0;
-    a.fan_rows = p->fan_rows;
-    a.fan_piece = p->fan_piece;
-    a.fault = p->d_fault;
-    PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
-    PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
-    PAX_REQUIRE(p->fan_piece >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
-                                   "(the z window of a single detector row exceeds its lanes)");
-    const bool plain = mode == PAX_AX_PLAIN;
-    if (p->fan_lq == 8)
-        return plain ? fan_launch<8, 16, FAN_NW8, PAX_AX_PLAIN>(a, count, st)
-                     : fan_launch<8, 16, FAN_NW8, PAX_AX_RESIDUAL>(a, count, st);
-    return plain ? fan_launch<4, 8, FAN_NW, PAX_AX_PLAIN>(a, count, st)
-                 : fan_launch<4, 8, FAN_NW, PAX_AX_RESIDUAL>(a, count, st);
 }

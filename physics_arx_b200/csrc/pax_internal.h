@@ -37,20 +37,15 @@ struct PaxPlan {
     AngleDev *d_angles;
     std::vector<AngleDev> h_angles;
     int projector;              // PAX_PROJECTOR_* requested (AUTO resolves per call)
-    int fan_rows;               // ax_fan.cu: detector rows one warp walks
-    int fan_piece;              // most rows summed from one set of tables (0: FAN does not fit the geometry)
-    int fan_fit;                // worst-case rows whose z window fits the lanes of a stream
-    int fan_lq;                 // lanes per step (4: 16-slice windows, 8: 32-slice windows)
+    // ax_fan.cu (fan-plane projector): launch shape and AUTO's criteria, from the geometry (pax_fan_configure)
+    int fan_rows;               // detector rows one warp walks
+    int fan_epoch;              // steps per epoch (0: the kernel does not fit the geometry)
+    int fan_cw;                 // steps per window (ring depth)
     int fan_warps;              // warps per CTA
+    int fan_minb;               // CTAs per SM the kernel is compiled for
+    int fan_fit;                // detector rows whose z range fits a warp's lanes over an epoch, worst case
     double fan_run;             // mean length (rows) of the equal-n runs of a detector column
-    int *d_fault;               // device word the fan kernel raises if a z window overflowed
-    // ax_fan_ev.cu (event-driven fan-plane kernel)
-    int fan_impl;               // 1: ax_fan_ev.cu (default), 0: ax_fan.cu (PAX_FAN_IMPL=old)
-    int fev_rows;               // detector rows one warp walks
-    int fev_epoch;              // steps per epoch (0: the kernel does not fit the geometry)
-    int fev_cw;                 // steps per window (ring depth)
-    int fev_warps;              // warps per CTA
-    int fev_minb;               // CTAs per SM the kernel is compiled for
+    int *d_fault;               // device word the fan kernel raises if a single row's z range overflowed its lanes
 };
 
 
@@ -78,18 +73,16 @@ struct AxArgs {
     float a0, a1, c;
     float whx, why, whz, wthr;
     int fan_rows;                 // ax_fan.cu: detector rows one warp walks
-    int fan_piece;                // ax_fan.cu: most rows that share one z window
-    int fan_epoch;                // ax_fan_ev.cu: steps per epoch
+    int fan_epoch;                // ax_fan.cu: steps per epoch
+    int fan_count;                // ax_fan.cu: angles of the launch
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
-    int *fault;                   // ax_fan.cu: set to 1 if a z window did not fit (never, by construction)
+    int *fault;                   // ax_fan.cu: set to 1 if a single row's z range did not fit the lanes (never, by construction)
 };
 
 // ax_fan.cu
 int pax_fan_configure(PaxPlan *p);
 int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a, int mode, int count, cudaStream_t st);
-// ax_fan_ev.cu
-int pax_fan_ev_configure(PaxPlan *p);
-int pax_ax_fan_ev_launch(const PaxPlan *p, const AxArgs &a, int mode, int count, cudaStream_t st);
+
 
 int pax_set_error(int code, const char *fmt, ...);
 

@@ -99,11 +99,6 @@ extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, Pax
     cudaMemset(p->d_fault, 0, sizeof(int));
     p->projector = PAX_PROJECTOR_AUTO;
     pax_fan_configure(p);
-    pax_fan_ev_configure(p);
-    {
-        const char *impl = getenv("PAX_FAN_IMPL");             // tuning hook: "old" = ax_fan.cu
-        p->fan_impl = (impl && strcmp(impl, "old") == 0) ? 0 : 1;
-    }
     *out = p;
     return PAX_OK;
 }
@@ -113,7 +108,7 @@ extern "C" int pax_plan_set_projector(PaxPlan *p, int kind)
     PAX_REQUIRE(p, "pax_plan_set_projector: NULL plan");
     PAX_REQUIRE(kind == PAX_PROJECTOR_AUTO || kind == PAX_PROJECTOR_RAY || kind == PAX_PROJECTOR_FAN,
                 "pax_plan_set_projector: unknown projector %d", kind);
-    PAX_REQUIRE(kind != PAX_PROJECTOR_FAN || p->fan_piece >= 1,
+    PAX_REQUIRE(kind != PAX_PROJECTOR_FAN || p->fan_epoch >= 1,
                 "pax_plan_set_projector: the fan-plane projector does not fit this geometry");
     p->projector = kind;
     return PAX_OK;
@@ -125,9 +120,10 @@ extern "C" int pax_plan_projector(const PaxPlan *p)
 {
     if (!p) return PAX_PROJECTOR_RAY;
     if (p->projector != PAX_PROJECTOR_AUTO) return p->projector;
-    // FAN pays when many rows share one lattice (long runs of equal n) and a piece of them fits the
-    // lanes; measured at C2 (mean run 154 rows, pieces of 64): 9.4 ms vs 18.6 ms per 20-angle subset
-    return (p->fan_fit >= 32 && p->fan_run >= 48.0) ? PAX_PROJECTOR_FAN : PAX_PROJECTOR_RAY;
+    // FAN pays when many rows share one lattice (long runs of equal n) and the rows fit a warp's lanes.  Measured
+    // with C2's volume and coarser and coarser detector rows (tools/bench_crossover.py, r2, fan / ray in ms per 20
+    // angles): mean run 154 rows 5.3 / 18.6; 51 rows 4.4 / 6.7; 38 rows 4.2 / 5.2; 26 rows 4.1 / 3.7
+    return (p->fan_fit >= 32 && p->fan_run >= 32.0) ? PAX_PROJECTOR_FAN : PAX_PROJECTOR_RAY;
 }
 
 extern "C" int pax_plan_fan_info(const PaxPlan *p, int *rows_per_tile, int *warps, double *mean_run)

@@ -118,7 +118,7 @@ class Plan:
 
     def check_fault(self):
         """Raise if the fan-plane projector flagged a launch whose z range did not fit its lanes (the results
-        of such a launch are wrong; pax_fan_ev_configure is meant to rule it out).  Synchronises the device."""
+        of such a launch are wrong; pax_fan_configure is meant to rule it out).  Synchronises the device."""
         if self.projector == "fan" and self.fault():
             raise _lib.PaxError("the fan-plane projector met a detector row whose z range does not fit its lanes "
                                 "on this geometry; use projector='ray' (PAX_AX_KERNEL=ray)")
