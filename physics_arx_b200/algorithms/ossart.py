@@ -21,7 +21,8 @@ import torch
 from .. import _lib
 from ..geometry import order_subsets
 from ..projector import Plan, _device_from_gpuids, _to_cuda
-from ..dist import choose_shard, row_window_geometry, shard_blocks, shard_rows, subset_geometry
+from ..dist import (band_axis, choose_shard, col_window_geometry, row_window_geometry, shard_blocks,
+                    shard_rows, subset_geometry)
 
 
 def _vp(t):
@@ -68,36 +69,43 @@ class OSSARTState:
         dev = proj.device if proj is not None else torch.device(
             "cuda", torch.cuda.current_device() if device is None else int(device))
         nv_full, nu = (int(v) for v in geo.nDetector)
-        # the ranks form an A x R grid: angles of every subset over A groups, detector rows over R bands
+        # the ranks form an A x R grid: the angles of every subset over A groups, the detector over R bands
+        # (of columns, or of rows with shard='rows')
         self.grid = choose_shard(self.blocks, self.world, shard) if self.world > 1 else (1, 1)
         A, R = self.grid
-        self.shard = "angles" if R == 1 else ("rows" if A == 1 else "grid")
+        self.axis = band_axis(shard)
+        self.shard = "angles" if R == 1 else (self.axis if A == 1 else "grid")
         ra, rr = self.rank % A, self.rank // A
-        self.v0, self.v1 = shard_rows(nv_full, rr, R) if R > 1 else (0, nv_full)
+        self.v0, self.v1, self.u0, self.u1 = 0, nv_full, 0, nu
+        if R > 1 and self.axis == "rows":
+            self.v0, self.v1 = shard_rows(nv_full, rr, R)
+        elif R > 1:
+            self.u0, self.u1 = shard_rows(nu, rr, R, align=8)     # whole 32-byte sectors of a projection row
         local, self.ranges = shard_blocks(self.blocks, ra, A)
-        empty = self.v1 <= self.v0
-        band = (0, 1) if empty else (self.v0, self.v1)          # keep a 1-row plan on an idle rank
+        empty = self.v1 <= self.v0 or self.u1 <= self.u0
         # a rank may own no angle at all (n < A): keep one dummy angle so a plan exists
         plan_idx = local if len(local) else np.array([0])
         plan_geo = subset_geometry(geo, plan_idx, n)
-        if R > 1:            # a band of detector rows is a detector of its own
-            plan_geo = row_window_geometry(plan_geo, *band)
+        if R > 1 and self.axis == "rows":       # a band of the detector is a detector of its own
+            plan_geo = row_window_geometry(plan_geo, *((0, 1) if empty else (self.v0, self.v1)))
+        elif R > 1:
+            plan_geo = col_window_geometry(plan_geo, *((0, 1) if empty else (self.u0, self.u1)))
         if empty:
             self.ranges = [(f, 0) for f, _ in self.ranges]
         self.local_idx = local
         self.plan = Plan(plan_geo, angles[plan_idx], device=dev.index)
         self.plan.w_geo = geo
-        n_own = len(local) if self.v1 > self.v0 else 0
-        rows = self.v1 - self.v0
-        full_rows = rows == nv_full
+        n_own = 0 if empty else len(local)
+        rows, cols = self.v1 - self.v0, self.u1 - self.u0
+        full = rows == nv_full and cols == nu
         if proj is None:                                    # caller fills the rank-local buffer
-            self.b = torch.empty((max(n_own, 1), max(rows, 1), nu), dtype=torch.float32,
+            self.b = torch.empty((max(n_own, 1), max(rows, 1), max(cols, 1)), dtype=torch.float32,
                                  device=dev)[:n_own]
-        elif len(local) == n and full_rows and np.array_equal(local, np.arange(n)):
+        elif len(local) == n and full and np.array_equal(local, np.arange(n)):
             self.b = proj                                   # ordered, single rank: no copy
         else:
             sel = proj[torch.as_tensor(local, device=dev, dtype=torch.long)] if n_own else proj[:0]
-            self.b = sel[:, self.v0:self.v1, :].contiguous()
+            self.b = sel[:, self.v0:self.v1, self.u0:self.u1].contiguous()
         # V_s (A.5): a sum over the subset's angles, so partial sums all-reduce exactly
         p = self.plan
         V = torch.zeros((len(self.blocks), p.ny, p.nx), dtype=torch.float32, device=dev)
@@ -131,12 +139,12 @@ class OSSARTState:
         all-reduce + local update when symmetric memory cannot be set up (no peer access, old torch)."""
         import ctypes
         import os
-        # PAX_FUSED_UPDATE: unset -> on from 8 ranks up (measured: 0.38 vs 0.47 ms per subset at C2 on 8 GPUs,
-        # but 0.05 ms slower than NCCL on 2); "0" off; "1" on (multicast when the fabric has it); "p2p" on, with
-        # peer pointers
+        # PAX_FUSED_UPDATE: unset -> on (it skips the columns no ray of the subset sees, about half of the plane,
+        # which an all-reduce cannot); "0" off: NCCL all-reduce + local update; "1" on (multicast when the fabric
+        # has it); "p2p" on, with peer pointers
         import torch.distributed as dist
         mode = os.environ.get("PAX_FUSED_UPDATE", "")
-        if not required and (mode == "0" or (mode == "" and self.world < 8)):
+        if not required and mode == "0":
             return
         if self.world > _lib.PAX_MAX_PEERS:        # the kernel's peer table (csrc/plan.cu); larger domains use NCCL
             if required:

@@ -298,16 +298,22 @@ template <bool MC>
 __global__ void __launch_bounds__(256) k_sart_update_fused(float *__restrict__ x_local, float *x_mc,
                                                            const float *upd_mc, const PeerPtrs peers, int world,
                                                            const float *__restrict__ inv_v, int nz, int ny, int nx,
-                                                           int nxp, int nzp, float lambda, int noneg, long t0,
-                                                           long t1)
+                                                           int nxp, int nzp, float lambda, int noneg, int rank,
+                                                           long n_local)
 {
+    // rank r owns the volume rows y = r, r + world, ...: whatever part of the plane a subset sees (a half disc
+    // whose orientation turns with the angles) is then spread evenly over the ranks
     const int nz4 = (nz + 3) / 4;
-    const long t = t0 + (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= t1) return;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_local) return;
     const int q = (int)(t % nz4);
-    const long col = t / nz4;
-    const int yy = (int)(col / nx), xx = (int)(col % nx);
+    const long cl = t / nz4;
+    const int yy = (int)(cl / nx) * world + rank, xx = (int)(cl % nx);
+    const long col = (long)yy * nx + xx;
     const float s = lambda * inv_v[col];
+    // a column no ray of this subset sees (V_s = 0: outside the half-fan's footprint, about half of the plane)
+    // gets no update: x stays what it is on every rank, and nothing has to cross the fabric for it
+    if (s == 0.f) return;
     const size_t base = ((size_t)(yy + 1) * nxp + (xx + 1)) * nzp + PAX_ZOFF + 4 * q;
     float4 b;
     if (MC) {
@@ -356,24 +362,24 @@ extern "C" int pax_sart_update_fused(const PaxPlan *p, float *x_local, float *x_
                 "pax_sart_update_fused: rank %d of %d", rank, world);
     const bool mc = x_mc && upd_mc;
     PAX_REQUIRE(mc || (x_peers && upd_peers), "pax_sart_update_fused: neither multicast nor peer pointers given");
-    const long n = (long)p->geo.nVoxelY * p->geo.nVoxelX * ((p->geo.nVoxelZ + 3) / 4);
-    const long t0 = n * rank / world, t1 = n * (rank + 1) / world;
-    if (t1 <= t0) return PAX_OK;
+    const long rows = (p->geo.nVoxelY - rank + world - 1) / world;          // rows y = rank (mod world)
+    const long n_local = rows * p->geo.nVoxelX * ((p->geo.nVoxelZ + 3) / 4);
+    if (n_local <= 0) return PAX_OK;
     PeerPtrs peers;
     for (int r = 0; r < PAX_MAX_PEERS; ++r) {
         peers.x[r] = (!mc && r < world) ? reinterpret_cast<float *>(x_peers[r]) : nullptr;
         peers.upd[r] = (!mc && r < world) ? reinterpret_cast<const float *>(upd_peers[r]) : nullptr;
     }
-    const int blocks = pax_cdiv(t1 - t0, 256);
+    const int blocks = pax_cdiv(n_local, 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (mc)
         k_sart_update_fused<true><<<blocks, 256, 0, st>>>(x_local, x_mc, upd_mc, peers, world, inv_v,
                                                          p->geo.nVoxelZ, p->geo.nVoxelY, p->geo.nVoxelX, p->nxp,
-                                                         p->nzp, lambda, noneg, t0, t1);
+                                                         p->nzp, lambda, noneg, rank, n_local);
     else
         k_sart_update_fused<false><<<blocks, 256, 0, st>>>(x_local, x_mc, upd_mc, peers, world, inv_v,
                                                           p->geo.nVoxelZ, p->geo.nVoxelY, p->geo.nVoxelX, p->nxp,
-                                                          p->nzp, lambda, noneg, t0, t1);
+                                                          p->nzp, lambda, noneg, rank, n_local);
     PAX_CHECK_CUDA(cudaGetLastError());
     return PAX_OK;
 }

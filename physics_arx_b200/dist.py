@@ -78,17 +78,39 @@ def row_window_geometry(geo, v0, v1, n_angles=None):
     return gs
 
 
+def col_window_geometry(geo, u0, u1):
+    """The detector columns [u0, u1) of `geo` as a geometry of their own (a pixel's u coordinate is
+    (u - nU/2 + 1/2) dU + offU, so the band is a detector of u1-u0 columns shifted in U).  Bilinear interpolation
+    across a band edge splits into two ramps that sum to one, exactly as for a band of rows."""
+    gs = geo.copy()
+    nu = int(np.asarray(geo.nDetector)[1])
+    du = float(np.asarray(geo.dDetector, dtype=np.float64)[1])
+    shift = (0.5 * (u0 + u1) - 0.5 * nu) * du
+    gs.nDetector = np.array((int(np.asarray(geo.nDetector)[0]), u1 - u0))
+    gs.sDetector = gs.nDetector * np.asarray(geo.dDetector, dtype=np.float64)
+    off = np.array(np.asarray(geo.offDetector, dtype=np.float64), copy=True)
+    off[..., 1] += shift
+    gs.offDetector = off
+    return gs
+
+
+def band_axis(shard):
+    """Which detector axis the bands of a grid cut: 'cols' (default: the fan-plane projector's work is per
+    detector column, so a band of columns costs its share and a band of rows costs the whole) or 'rows'."""
+    return "rows" if shard == "rows" else "cols"
+
+
 def choose_shard(blocks, world, shard="auto"):
     """(A, R): the ranks form an A x R grid -- the angles of every subset are interleaved over A groups and
     every group splits the detector rows into R bands; rank r sits at (r % A, r // A).
 
       'angles' -> (world, 1)   the prescribed scheme
-      'rows'   -> (1, world)
+      'rows'   -> (1, world)   bands of detector rows
+      'cols'   -> (1, world)   bands of detector columns
       'grid' / 'auto' -> A = gcd(world, every subset's size), R = world / A: every rank gets the same
-                number of angles in every subset, and the row bands stay as tall as possible (the
-                fan-plane projector shares its work along detector columns).  Blocksize 20 with a tail
-                of 16 over 8 ranks gives 4 x 2: 5 (4) angles x half the rows per rank, instead of 3,3,3,3,
-                2,2,2,2 whole projections.  Measured at C2 on 8 x B200 (r1): see DESIGN.md section 6.
+                number of angles in every subset; the bands cut the detector COLUMNS (band_axis).
+                Blocksize 20 with a tail of 16 over 8 ranks gives 4 x 2: 5 (4) angles x half the columns per
+                rank, instead of 3,3,3,3,2,2,2,2 whole projections.  See DESIGN.md section 6.
     """
     if isinstance(shard, (tuple, list)):                    # an explicit grid
         a, r = (int(v) for v in shard)
@@ -97,7 +119,7 @@ def choose_shard(blocks, world, shard="auto"):
         return a, r
     if shard == "angles":
         return world, 1
-    if shard == "rows":
+    if shard in ("rows", "cols"):
         return 1, world
     if shard not in ("auto", "grid"):
         raise ValueError(f"unknown shard mode {shard!r}")

@@ -76,20 +76,28 @@ class SCBCTPipeline:
         if self.group is not None:
             dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
         # noise is keyed by the GLOBAL pixel index, so the result does not depend on the sharding
-        nu = p.nu
+        nu_full = int(np.asarray(self.geo.nDetector)[1])
         nv_full = int(np.asarray(self.geo.nDetector)[0])
-        npix = nv_full * nu
+        npix = nv_full * nu_full
         lib = p.lib
-        rows = st.v1 - st.v0
-        inner = 0 if rows == nv_full else rows * nu      # a band of rows: [angles][rows*nu] cut out of [angles][npix]
+        rows, cols = st.v1 - st.v0, st.u1 - st.u0
+        # the rank's buffer as runs of `inner` consecutive global pixels, `stride` apart: whole projections, a
+        # band of rows ([angles][rows*nu] out of [angles][npix]) or a band of columns ([angles*rows][cols] out
+        # of rows of nu)
+        if cols != nu_full:
+            inner, stride, first = cols, nu_full, st.u0
+        elif rows != nv_full:
+            inner, stride, first = rows * nu_full, npix, st.v0 * nu_full
+        else:
+            inner, stride, first = 0, 0, 0
         with torch.cuda.device(self.device):
             pos = 0
             if self.n_local:
                 for g0, cnt in _contiguous_runs(self.local_idx):      # runs of consecutive global angles
                     view = st.b[pos:pos + cnt]
                     _lib.check(lib.pax_ctnoise(_ptr(view), view.numel(),
-                                               ctypes.c_uint64(int(g0) * npix + st.v0 * nu), inner,
-                                               ctypes.c_uint64(npix if inner else 0), self.I0, 0.0,
+                                               ctypes.c_uint64(int(g0) * npix + first), inner,
+                                               ctypes.c_uint64(stride), self.I0, 0.0,
                                                self.sigma, _ptr(m), ctypes.c_uint64(self.seed), _stream()),
                                "pax_ctnoise")
                     self.launches += 1

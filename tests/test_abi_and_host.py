@@ -191,9 +191,12 @@ def test_choose_shard_auto():
     from physics_arx_b200.dist import choose_shard
     blocks = order_subsets(656, 20)                      # 32 x 20 + 16
     assert choose_shard(blocks, 2) == (2, 1) and choose_shard(blocks, 4) == (4, 1)      # plain angle sharding
-    assert choose_shard(blocks, 8) == (4, 2)             # 5 (4) angles x half the rows on every rank
-    assert choose_shard(order_subsets(40, 7), 4) == (1, 4)   # 7 and 5 angles share no factor with 4: row bands
+    assert choose_shard(blocks, 8) == (4, 2)             # 5 (4) angles x half the detector columns on every rank
+    assert choose_shard(order_subsets(40, 7), 4) == (1, 4)   # 7 and 5 angles share no factor with 4: bands only
     assert choose_shard(blocks, 8, "angles") == (8, 1) and choose_shard(blocks, 8, "rows") == (1, 8)
+    assert choose_shard(blocks, 8, "cols") == (1, 8)
+    from physics_arx_b200.dist import band_axis
+    assert band_axis("auto") == band_axis("grid") == band_axis((4, 2)) == "cols" and band_axis("rows") == "rows"
     assert choose_shard(blocks, 8, (2, 4)) == (2, 4)
     with pytest.raises(ValueError):
         choose_shard(blocks, 8, (3, 2))
@@ -230,9 +233,37 @@ def test_row_band_is_a_detector_of_its_own(oracle):
     assert full_w.shape == (4, 22, 30)
 
 
+def test_column_band_is_a_detector_of_its_own(oracle):
+    """Ax of a band of detector columns == those columns of the full Ax; Atb / V over the bands sum to the
+    full Atb / V (what the grid sharding of the GPUs relies on)."""
+    from conftest import rel_l2
+    from physics_arx_b200.dist import col_window_geometry, shard_rows
+    from physics_arx_b200.phantom import make_geometry
+    geo = make_geometry((8, 16, 16), (14.0, 9.0, 9.0), (22, 30), (8.0, 7.0), off_detector=(3.0, -25.0))
+    ang = np.array([0.2, 1.9, 3.3, 5.0])
+    rng = np.random.default_rng(4)
+    vol = rng.random((8, 16, 16))
+    proj = rng.standard_normal((4, 22, 30))
+    full_ax, full_atb = oracle.ax(vol, geo, ang), oracle.atb(proj, geo, ang)
+    full_v = oracle.atb(None, geo, ang, vscale=geo.v_scale())
+    acc, vacc = 0.0, 0.0
+    for r in range(3):
+        u0, u1 = shard_rows(30, r, 3, align=8)
+        gb = col_window_geometry(geo, u0, u1)
+        assert tuple(gb.nDetector) == (22, u1 - u0)
+        assert rel_l2(oracle.ax(vol, gb, ang), full_ax[:, :, u0:u1]) < 1e-12
+        acc = acc + oracle.atb(proj[:, :, u0:u1], gb, ang)
+        vacc = vacc + oracle.atb(None, gb, ang, vscale=geo.v_scale())
+        # the 'matlab' W box depends on sDetector's ROW extent only, so a band of columns keeps it (the plans of
+        # the ranks take the box from the full geometry anyway: Plan.w_geo)
+        assert np.allclose(gb.w_box("matlab")[0], geo.w_box("matlab")[0])
+    assert rel_l2(acc, full_atb) < 1e-12
+    assert rel_l2(vacc, full_v) < 1e-12
+
+
 @pytest.mark.parametrize("world,nv,blocksize,n", [(8, 768, 20, 656), (4, 96, 6, 40), (6, 50, 9, 45), (2, 33, 5, 23)])
 def test_grid_sharding_covers_every_ray_once(world, nv, blocksize, n):
-    """(angle groups) x (row bands): over all ranks, every (angle, detector row) of every subset is owned
+    """(angle groups) x (detector bands): over all ranks, every (angle, band unit) of every subset is owned
     exactly once, and with the auto grid every rank gets the same number of angles in every subset."""
     from physics_arx_b200 import order_subsets
     from physics_arx_b200.dist import choose_shard, shard_blocks, shard_rows

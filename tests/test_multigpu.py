@@ -33,16 +33,21 @@ def _worker(rank, world, port, q, shard):
     art = artifact_volume(geo.nVoxel, seed=1)
     kw = dict(niter=3, blocksize=5, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=3)
     want = "nccl"
+    os.environ["PAX_FUSED_UPDATE"] = "0"    # the plain modes below exercise NCCL all-reduce + local update
     if shard == "p2p":                      # the peer-pointer variant of the fused update kernel
         os.environ["PAX_FUSED_UPDATE"] = "p2p"
         shard, want = "angles", "peer pointers"
     elif shard == "fused":                  # the fused kernel, multicast when the fabric has it
         os.environ["PAX_FUSED_UPDATE"] = "1"
         shard, want = "grid", "fused"
-    if shard == "grid":                     # 2 angle groups x (world/2) row bands
+    elif shard == "default":                # what a caller gets: the fused kernel, auto grid
+        del os.environ["PAX_FUSED_UPDATE"]
+        shard, want = "auto", "fused"
+    if shard == "grid":                     # 2 angle groups x (world/2) bands of detector columns
         shard = (2, world // 2)
     pipe = SCBCTPipeline(geo, angles, group=dist.group.WORLD, shard=shard, **kw)
-    assert pipe.st.shard == (shard if isinstance(shard, str) else ("grid" if world > 2 else "angles"))
+    if shard != "auto":
+        assert pipe.st.shard == (shard if isinstance(shard, str) else ("grid" if world > 2 else "angles"))
     sharded = pipe.run_host(ct, art).numpy().copy()
     coll = "nccl" if pipe.st.fused is None else pipe.st.fused["kind"]
     if want == "fused":
@@ -67,7 +72,7 @@ def _worker(rank, world, port, q, shard):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("shard", ["angles", "rows", "grid", "p2p", "fused"])
+@pytest.mark.parametrize("shard", ["angles", "rows", "cols", "grid", "p2p", "fused", "default"])
 def test_sharded_pipeline_equals_single_gpu(shard):
     import torch
     n = torch.cuda.device_count()
