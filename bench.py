@@ -152,7 +152,7 @@ def run_reference(args, cfg, rank):
             "gpu_launches": 0,
             "note": "the reference has no CPU implementation of this path (TIGRE is CUDA-only, un-vendored); "
                     "this arm times the build's float64 oracle on the host cores, each step a bounded sample"}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------- multi-GPU parity (untimed)
@@ -309,6 +309,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     pipe.launches = 0
     pipe.st.kernel_events = []
+    pipe.st.phase_events = {}
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -320,6 +321,7 @@ def main():
     launches = pipe.launches
     events = pipe.st.kernel_events
     pipe.st.kernel_events = None
+    phases = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in pipe.st.phase_events.items()}
     ax_ms = [a.elapsed_time(b) for a, b, _ in events]
     ax_counts = [c for _, _, c in events]
     clocks = sampler.stop() if sampler else None
@@ -396,6 +398,10 @@ def main():
                          "note": "issue- and latency-bound gather + prefix sums, not HBM-bound: see "
                                  "ax_gsamples_per_s and profiles/"},
             "gpu_launches": launches,
+            "subset_step_ms": dict(ax=float(np.mean(ax_ms)) if ax_ms else None, **phases,
+                                   total=(ms / args.steps) / max(cfg["niter"] * len(pipe.st.blocks), 1),
+                                   note="rank 0, CUDA events around each phase of an OS-SART subset step; total = "
+                                        "whole step / subset steps (includes the simulation pass and all gaps)"),
             "clocks": clocks,
             "ax_gsamples_per_s": (samples_resid / (sum(ax_ms) * 1e-3) / 1e9) if ax_ms else None,
             "ax_samples_per_full_pass": total_samples_per_pass,
@@ -414,7 +420,7 @@ def main():
                 line["secondary"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample(cfg)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

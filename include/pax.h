@@ -120,6 +120,11 @@ int pax_plan_projector(const PaxPlan *plan);
  * warp over one epoch in the worst case (0 = the kernel does not fit), warps per CTA, mean length in rows
  * of the runs that share one lattice */
 int pax_plan_fan_info(const PaxPlan *plan, int *rows_per_tile, int *warps, double *mean_run);
+/* Multi-GPU: restrict the FAN kernel of this plan to share `part` of `parts` of the detector's column tiles
+ * (dealt out by decreasing chord length, so the shares cost the same).  pax_ax then reads / writes only the
+ * columns of its share; the others keep what the caller put there (zeros, for the backprojection of a
+ * partial residual to be exact).  parts = 1 restores the whole detector. */
+int pax_plan_set_column_share(PaxPlan *plan, int part, int parts);
 /* self-check of the FAN kernel: 1 if any launch so far met a single detector row whose z range over an
  * epoch is wider than its 32 lanes (the epoch length is derived so that this cannot happen; the results
  * of such a launch are wrong); synchronises the device */

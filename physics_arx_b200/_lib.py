@@ -50,6 +50,7 @@ SYMBOLS = [
     ("pax_plan_n_angles", ctypes.c_int, [_VP]),
     ("pax_plan_set_projector", ctypes.c_int, [_VP, ctypes.c_int]),
     ("pax_plan_projector", ctypes.c_int, [_VP]),
+    ("pax_plan_set_column_share", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int]),
     ("pax_plan_fan_info", ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                          c_double_p]),
     ("pax_plan_fault", ctypes.c_int, [_VP]),

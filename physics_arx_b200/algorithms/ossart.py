@@ -82,24 +82,41 @@ class OSSARTState:
         elif R > 1:
             self.u0, self.u1 = shard_rows(nu, rr, R, align=8)     # whole 32-byte sectors of a projection row
         local, self.ranges = shard_blocks(self.blocks, ra, A)
-        empty = self.v1 <= self.v0 or self.u1 <= self.u0
         # a rank may own no angle at all (n < A): keep one dummy angle so a plan exists
         plan_idx = local if len(local) else np.array([0])
-        plan_geo = subset_geometry(geo, plan_idx, n)
-        if R > 1 and self.axis == "rows":       # a band of the detector is a detector of its own
-            plan_geo = row_window_geometry(plan_geo, *((0, 1) if empty else (self.v0, self.v1)))
-        elif R > 1:
-            plan_geo = col_window_geometry(plan_geo, *((0, 1) if empty else (self.u0, self.u1)))
+        sub_geo = subset_geometry(geo, plan_idx, n)
+        self.tiles = None              # (part, parts): this rank's share of the detector's column tiles
+        plan = None
+        if R > 1 and self.axis == "cols":
+            # Where the fan-plane projector runs, the bands are not contiguous: every rank keeps the WHOLE detector
+            # and its kernel walks every R-th column tile, dealt out by decreasing chord length -- contiguous bands
+            # of a half-fan detector differ by 1.5x in work.  The columns of the other ranks stay zero in the
+            # residual, so the backprojections of the ranks still add up exactly.
+            plan = Plan(sub_geo, angles[plan_idx], device=dev.index)
+            if plan.projector == "fan" and shard != "cols":    # (shard='cols' asks for contiguous bands)
+                plan.set_column_share(rr, R)
+                self.tiles = (rr, R)
+                self.u0, self.u1 = 0, nu
+            else:
+                plan = None
+        empty = self.v1 <= self.v0 or self.u1 <= self.u0
+        plan_geo = sub_geo
+        if plan is None:
+            if R > 1 and self.axis == "rows":       # a band of the detector is a detector of its own
+                plan_geo = row_window_geometry(sub_geo, *((0, 1) if empty else (self.v0, self.v1)))
+            elif R > 1:
+                plan_geo = col_window_geometry(sub_geo, *((0, 1) if empty else (self.u0, self.u1)))
+            plan = Plan(plan_geo, angles[plan_idx], device=dev.index)
         if empty:
             self.ranges = [(f, 0) for f, _ in self.ranges]
         self.local_idx = local
-        self.plan = Plan(plan_geo, angles[plan_idx], device=dev.index)
+        self.plan = plan
         self.plan.w_geo = geo
         n_own = 0 if empty else len(local)
         rows, cols = self.v1 - self.v0, self.u1 - self.u0
         full = rows == nv_full and cols == nu
         if proj is None:                                    # caller fills the rank-local buffer
-            self.b = torch.empty((max(n_own, 1), max(rows, 1), max(cols, 1)), dtype=torch.float32,
+            self.b = torch.zeros((max(n_own, 1), max(rows, 1), max(cols, 1)), dtype=torch.float32,
                                  device=dev)[:n_own]
         elif len(local) == n and full and np.array_equal(local, np.arange(n)):
             self.b = proj                                   # ordered, single rank: no copy
@@ -113,6 +130,8 @@ class OSSARTState:
             for s, (first, count) in enumerate(self.ranges):
                 if count:
                     p.compute_v(first, count, out=V[s])
+            if self.tiles is not None:      # every rank of an angle group computed the whole detector's map
+                V /= self.tiles[1]
         elif v_variant == "B":
             V.copy_(torch.from_numpy(_v_variant_b(geo, angles, self.blocks)).to(dev))
             if self.world > 1:
@@ -123,7 +142,8 @@ class OSSARTState:
             dist.all_reduce(V, group=self.group)
         self.inv_v = torch.where(V > 1e-12, 1.0 / V, torch.zeros_like(V)).contiguous()
         self.max_count = max((c for _, c in self.ranges), default=0)
-        self.resid = torch.empty((max(self.max_count, 1), p.nv, p.nu), dtype=torch.float32, device=dev)
+        # (zeros: with a share of the column tiles the other ranks' columns are never written and must read 0)
+        self.resid = torch.zeros((max(self.max_count, 1), p.nv, p.nu), dtype=torch.float32, device=dev)
         self.upd = p.new_volume() if self.world > 1 else None
         self.fused = None              # symmetric-memory state of the fused reduce + update + broadcast
         if self.world > 1 and fused_update is not False:
@@ -131,6 +151,7 @@ class OSSARTState:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.launches = 0              # kernels of libpax launched by subset_step (bench claim)
         self.kernel_events = None      # set to [] to record CUDA events around the Ax kernel
+        self.phase_events = {}         # ... and around the other phases of a subset step (bench breakdown)
 
     # ------------------------------------------------- fused collective (csrc/plan.cu: k_sart_update_fused)
     def _setup_fused(self, dev, required=False):
@@ -198,6 +219,17 @@ class OSSARTState:
             return self.fused["x"]
         return self.plan.new_volume()
 
+    def _timed(self, name, fn):
+        """Run fn(); with kernel_events enabled also bracket it with CUDA events under `name` (bench breakdown)."""
+        if self.kernel_events is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.phase_events.setdefault(name, []).append((e0, e1))
+        return out
+
     def subset_step(self, x_res, s, lam, noneg=True, computel2=False):
         import torch.distributed as dist
         p = self.plan
@@ -216,7 +248,8 @@ class OSSARTState:
             self.launches += p.ax_launches(1)                  # (quad re-pack +) projector
         if self.world == 1:
             if count <= _lib.PAX_ATB_SART_MAX:
-                p.atb(self.resid, first, count, x_res, _lib.PAX_ATB_SART, self.inv_v[s], lam, noneg)
+                self._timed("atb", lambda: p.atb(self.resid, first, count, x_res, _lib.PAX_ATB_SART,
+                                                 self.inv_v[s], lam, noneg))
                 self.launches += 1
             else:
                 # a block larger than the fused kernel's angle table (TIGRE takes any blocksize, SIRT
@@ -229,23 +262,23 @@ class OSSARTState:
                 self.launches += 1 + -(-count // _lib.PAX_ATB_SART_MAX)
             return
         if count:
-            p.atb(self.resid, first, count, self.upd, _lib.PAX_ATB_STORE)
+            self._timed("atb", lambda: p.atb(self.resid, first, count, self.upd, _lib.PAX_ATB_STORE))
             self.launches += 1
         else:
             self.upd.zero_()
         f = self.fused
         if f is not None and x_res.data_ptr() == f["x"].data_ptr():
             # one kernel: reduce the partial updates over the ranks, update my slice, write it to every rank
-            f["hu"].barrier(channel=0)                     # every rank's partial update is complete
-            _lib.check(p.lib.pax_sart_update_fused(
+            self._timed("barrier", lambda: f["hu"].barrier(channel=0))      # every rank's partial update is complete
+            self._timed("update", lambda: _lib.check(p.lib.pax_sart_update_fused(
                 p._h, _vp(x_res), _vp_int(f["mc_x"]), _vp_int(f["mc_u"]), f["x_peers"], f["upd_peers"],
                 self.rank, self.world, _vp(self.inv_v[s]), float(lam), int(bool(noneg)), _cur_stream()),
-                "pax_sart_update_fused")
-            f["hx"].barrier(channel=0)                     # every slice has landed everywhere
+                "pax_sart_update_fused"))
+            self._timed("barrier", lambda: f["hx"].barrier(channel=0))      # every slice has landed everywhere
             self.launches += 1
             return
-        dist.all_reduce(self.upd, group=self.group)
-        p.sart_update(x_res, self.upd, self.inv_v[s], lam, noneg)
+        self._timed("update", lambda: (dist.all_reduce(self.upd, group=self.group),
+                                       p.sart_update(x_res, self.upd, self.inv_v[s], lam, noneg)))
         self.launches += 1
 
     def iteration(self, x_res, lam, noneg=True, computel2=False):

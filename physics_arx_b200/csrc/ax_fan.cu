@@ -31,6 +31,7 @@
 // accumulates and 2 STS.128 of its running (A, C) into a ring of CW steps.  After every CW steps the lanes
 // enumerate the rows that crossed their boundaries (closed form: a row interval per boundary), and the warp
 // serves those events 32 at a time from the ring; at the end of an epoch every row reads its pair once.
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -138,7 +139,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     // CTA order: angle fastest, then the column tile.  The angles of a launch are a few degrees apart, so at any
     // time the resident CTAs walk chords through one narrow bow-tie of the volume, which stays in L2 while the
     // bow-tie sweeps across (column-tile-fastest order re-read the volume from DRAM once per angle)
-    const int u = (blockIdx.x / a.fan_count) * NWARPS + warp;
+    // Column tiles in order of decreasing chord length (a.fan_order): a warp walks its column alone, so a long
+    // chord that starts in the last wave of CTAs would keep the launch waiting with most of the SMs idle
+    const int u = a.fan_order[blockIdx.x / a.fan_count] * NWARPS + warp;
     if (u >= a.nu) return;                                        // warps are independent: no CTA barriers below
     const int ia = blockIdx.x % a.fan_count;
     const int V0 = blockIdx.y * a.fan_rows;
@@ -559,7 +562,8 @@ static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AxArgs b = a;
     b.fan_count = count;
-    dim3 grid(pax_cdiv(a.nu, NWARPS) * count, pax_cdiv(a.nv, a.fan_rows));
+    dim3 grid(a.fan_ntiles * count, pax_cdiv(a.nv, a.fan_rows));
+    if (a.fan_ntiles == 0) return PAX_OK;
     k_ax_fan<CW, NWARPS, MINB, MODE><<<grid, NWARPS * 32, smem, st>>>(b);
     return PAX_OK;
 }
@@ -577,6 +581,9 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     a.fan_rows = p->fan_rows;
     a.fan_epoch = p->fan_epoch;
     a.fault = p->d_fault;
+    a.fan_order = p->d_fan_order;
+    a.fan_ntiles = p->fan_ntiles;
+    PAX_REQUIRE(a.fan_order, "pax_ax: the fan-plane projector was not configured for this plan");
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
     PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
     PAX_REQUIRE(p->fan_epoch >= 1, "pax_ax: the fan-plane projector does not fit this geometry "
@@ -623,6 +630,33 @@ int pax_fan_configure(PaxPlan *p)
     p->fan_warps = nw;
     const int tiles = (g.nDetecV + FAN_MAXROWS - 1) / FAN_MAXROWS;
     p->fan_rows = (g.nDetecV + tiles - 1) / tiles;
+    // launch order of the column tiles: longest chords first (mean over a few of the plan's angles of the in-plane
+    // chord through the volume's box, summed over the tile's columns)
+    {
+        const int ntile = (g.nDetecU + nw - 1) / nw;
+        std::vector<double> cost(ntile, 0.0);
+        const int na = (int)p->h_angles.size(), nsamp = std::min(na, 8);
+        for (int s = 0; s < nsamp; ++s) {
+            const AngleDev &A = p->h_angles[(size_t)s * na / nsamp];
+            for (int u = 0; u < g.nDetecU; ++u) {
+                const double dx = A.ox + u * A.ux - A.sx, dy = A.oy + u * A.uy - A.sy;
+                double t0 = 0.0, t1 = 1.0;
+                bool hit = true;
+                const double lo = 0.0, hx = g.nVoxelX + 1.0, hy = g.nVoxelY + 1.0;
+                if (dx == 0.0) hit = hit && A.sx >= lo && A.sx < hx;
+                else { const double a0 = (lo - A.sx) / dx, a1 = (hx - A.sx) / dx;
+                       t0 = std::fmax(t0, std::fmin(a0, a1)); t1 = std::fmin(t1, std::fmax(a0, a1)); }
+                if (dy == 0.0) hit = hit && A.sy >= lo && A.sy < hy;
+                else { const double a0 = (lo - A.sy) / dy, a1 = (hy - A.sy) / dy;
+                       t0 = std::fmax(t0, std::fmin(a0, a1)); t1 = std::fmin(t1, std::fmax(a0, a1)); }
+                if (hit && t1 > t0) cost[u / nw] += (t1 - t0) * std::sqrt(dx * dx + dy * dy);
+            }
+        }
+        p->h_fan_order.resize(ntile);
+        for (int t = 0; t < ntile; ++t) p->h_fan_order[t] = t;
+        std::stable_sort(p->h_fan_order.begin(), p->h_fan_order.end(),
+                         [&](int a_, int b_) { return cost[a_] > cost[b_]; });
+    }
     // AUTO's criteria (pax_plan_projector, pax_plan_fan_info): how many detector rows fit the 32 lanes of a warp
     // over one epoch in the worst case, and how long the runs of equal n are (what the sharing is worth)
     {

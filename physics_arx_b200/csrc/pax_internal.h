@@ -46,6 +46,10 @@ struct PaxPlan {
     int fan_fit;                // detector rows whose z range fits a warp's lanes over an epoch, worst case
     double fan_run;             // mean length (rows) of the equal-n runs of a detector column
     int *d_fault;               // device word the fan kernel raises if a single row's z range overflowed its lanes
+    std::vector<int> h_fan_order;   // column tiles (fan_warps columns each) sorted by decreasing chord length
+    int *d_fan_order;               // the tiles this plan's launches walk (all of them, or its share)
+    int fan_ntiles;                 // how many
+    int fan_share_part, fan_share_parts;   // pax_plan_set_column_share
 };
 
 
@@ -75,6 +79,8 @@ struct AxArgs {
     int fan_rows;                 // ax_fan.cu: detector rows one warp walks
     int fan_epoch;                // ax_fan.cu: steps per epoch
     int fan_count;                // ax_fan.cu: angles of the launch
+    const int *fan_order;         // ax_fan.cu: column tiles in launch order (longest chords first)
+    int fan_ntiles;               // ax_fan.cu: how many of them
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
     int *fault;                   // ax_fan.cu: set to 1 if a single row's z range did not fit the lanes (never, by construction)
 };

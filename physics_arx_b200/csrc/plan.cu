@@ -98,7 +98,24 @@ extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, Pax
     p->d_fault = reinterpret_cast<int *>(p->d_angles + n);       // same allocation, after the angles
     cudaMemset(p->d_fault, 0, sizeof(int));
     p->projector = PAX_PROJECTOR_AUTO;
+    p->d_fan_order = nullptr;
+    p->fan_share_part = 0;
+    p->fan_share_parts = 1;
     pax_fan_configure(p);
+    p->fan_ntiles = (int)p->h_fan_order.size();
+    if (!p->h_fan_order.empty()) {
+        // the fan-plane kernel's column tiles, longest chords first (ax_fan.cu: tail of the last wave)
+        e = cudaMalloc(&p->d_fan_order, sizeof(int) * p->h_fan_order.size());
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->d_fan_order, p->h_fan_order.data(), sizeof(int) * p->h_fan_order.size(),
+                           cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (p->d_fan_order) cudaFree(p->d_fan_order);
+            cudaFree(p->d_angles);
+            delete p;
+            return pax_set_error(PAX_ERR_CUDA, "pax_plan_create: %s", cudaGetErrorString(e));
+        }
+    }
     *out = p;
     return PAX_OK;
 }
@@ -126,6 +143,29 @@ extern "C" int pax_plan_projector(const PaxPlan *p)
     return (p->fan_fit >= 32 && p->fan_run >= 32.0) ? PAX_PROJECTOR_FAN : PAX_PROJECTOR_RAY;
 }
 
+// The fan-plane projector of this plan works on every `parts`-th column tile only (tiles dealt out in order of
+// decreasing cost, back and forth, so that the shares are balanced): how the ranks of a multi-GPU run split the
+// detector columns of an angle between them.  Columns outside the share are neither read nor written by pax_ax.
+extern "C" int pax_plan_set_column_share(PaxPlan *p, int part, int parts)
+{
+    PAX_REQUIRE(p, "pax_plan_set_column_share: NULL plan");
+    PAX_REQUIRE(parts >= 1 && part >= 0 && part < parts, "pax_plan_set_column_share: share %d of %d", part, parts);
+    PAX_REQUIRE(!p->h_fan_order.empty() && p->fan_epoch >= 1,
+                "pax_plan_set_column_share: the fan-plane projector does not fit this geometry");
+    std::vector<int> mine;
+    const int n = (int)p->h_fan_order.size();
+    for (int i = 0; i < n; ++i) {
+        const int round = i / parts, pos = i % parts;
+        if (((round & 1) ? parts - 1 - pos : pos) == part) mine.push_back(p->h_fan_order[i]);
+    }
+    p->fan_share_part = part;
+    p->fan_share_parts = parts;
+    p->fan_ntiles = (int)mine.size();
+    if (!mine.empty())
+        PAX_CHECK_CUDA(cudaMemcpy(p->d_fan_order, mine.data(), sizeof(int) * mine.size(), cudaMemcpyHostToDevice));
+    return PAX_OK;
+}
+
 extern "C" int pax_plan_fan_info(const PaxPlan *p, int *rows_per_tile, int *warps, double *mean_run)
 {
     PAX_REQUIRE(p, "pax_plan_fan_info: NULL plan");
@@ -148,6 +188,7 @@ extern "C" int pax_plan_destroy(PaxPlan *p)
 {
     if (!p) return PAX_OK;
     if (p->d_angles) cudaFree(p->d_angles);
+    if (p->d_fan_order) cudaFree(p->d_fan_order);
     delete p;
     return PAX_OK;
 }

@@ -114,6 +114,8 @@ class SCBCTPipeline:
                 if count:
                     p.compute_v(first, count, out=V[s])
                     self.launches += 1
+            if st.tiles is not None:
+                V /= st.tiles[1]
             if st.world > 1:
                 dist.all_reduce(V, group=st.group)
             st.inv_v = torch.where(V > 1e-12, 1.0 / V, torch.zeros_like(V)).contiguous()

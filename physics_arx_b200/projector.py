@@ -106,6 +106,11 @@ class Plan:
         return {_lib.PAX_PROJECTOR_RAY: "ray", _lib.PAX_PROJECTOR_FAN: "fan"}[
             int(self.lib.pax_plan_projector(self._h))]
 
+    def set_column_share(self, part, parts):
+        """Multi-GPU: the fan-plane kernel of this plan walks share `part` of `parts` of the detector's column
+        tiles only (include/pax.h: pax_plan_set_column_share)."""
+        _lib.check(self.lib.pax_plan_set_column_share(self._h, int(part), int(parts)), "pax_plan_set_column_share")
+
     def fan_info(self):
         rows, warps, run = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
         _lib.check(self.lib.pax_plan_fan_info(self._h, ctypes.byref(rows), ctypes.byref(warps),

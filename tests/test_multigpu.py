@@ -28,6 +28,9 @@ def _worker(rank, world, port, q, shard):
     from physics_arx_b200.phantom import artifact_volume, lung_phantom, make_geometry
     from physics_arx_b200.pipeline import SCBCTPipeline
     geo = make_geometry((16, 40, 40), (10.0, 6.0, 6.0), (40, 72), (6.0, 4.0), off_detector=(0.0, -30.0))
+    if shard == "tiles":                    # fine rows over thick slices: AUTO picks the fan-plane projector, and
+        # the bands of a grid become shares of its column tiles (OSSARTState.tiles)
+        geo = make_geometry((16, 40, 40), (10.0, 4.0, 4.0), (160, 72), (1.5, 4.0), off_detector=(0.0, -30.0))
     angles = np.linspace(0, 2 * np.pi, 23)
     ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
     art = artifact_volume(geo.nVoxel, seed=1)
@@ -40,13 +43,18 @@ def _worker(rank, world, port, q, shard):
     elif shard == "fused":                  # the fused kernel, multicast when the fabric has it
         os.environ["PAX_FUSED_UPDATE"] = "1"
         shard, want = "grid", "fused"
+    elif shard == "tiles":
+        del os.environ["PAX_FUSED_UPDATE"]
+        shard, want = (1, world), "fused"
     elif shard == "default":                # what a caller gets: the fused kernel, auto grid
         del os.environ["PAX_FUSED_UPDATE"]
         shard, want = "auto", "fused"
     if shard == "grid":                     # 2 angle groups x (world/2) bands of detector columns
         shard = (2, world // 2)
     pipe = SCBCTPipeline(geo, angles, group=dist.group.WORLD, shard=shard, **kw)
-    if shard != "auto":
+    if want == "fused" and isinstance(shard, tuple) and shard[0] == 1:
+        assert pipe.st.tiles == (dist.get_rank(), world) and pipe.plan.projector == "fan"
+    elif shard != "auto":
         assert pipe.st.shard == (shard if isinstance(shard, str) else ("grid" if world > 2 else "angles"))
     sharded = pipe.run_host(ct, art).numpy().copy()
     coll = "nccl" if pipe.st.fused is None else pipe.st.fused["kind"]
@@ -72,7 +80,7 @@ def _worker(rank, world, port, q, shard):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("shard", ["angles", "rows", "cols", "grid", "p2p", "fused", "default"])
+@pytest.mark.parametrize("shard", ["angles", "rows", "cols", "grid", "p2p", "fused", "default", "tiles"])
 def test_sharded_pipeline_equals_single_gpu(shard):
     import torch
     n = torch.cuda.device_count()

@@ -10,12 +10,12 @@ echo "== pytest tests/test_multigpu.py"
 timeout 900 python -m pytest tests/test_multigpu.py -q -m gpu -s 2>&1 | tail -15
 fi
 echo "== bench N=$N"
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N $BENCH_ARGS > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N $BENCH_ARGS > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:
-    d = json.load(open('gpurun_out/bench_$TAG.json'))
-    print('ms_per_step', d['ms_per_step'], 'ax ms', d['roofline']['avg_launch_ms'], 'sharding', d.get('sharding'))
+    d = [json.loads(l) for l in open('gpurun_out/bench_$TAG.json') if l.startswith('{')][-1]
+    print('ms_per_step', d['ms_per_step'], 'phases', d.get('subset_step_ms'), 'sharding', (d.get('sharding') or {}).get('grid'))
     print('parity', json.dumps(d.get('parity_vs_1gpu')))
 except Exception as e:
     print('bench failed', e)
