@@ -155,6 +155,85 @@ def run_reference(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------- GPU-vs-GPU anchor: the recalled TIGRE launch shapes on this GPU
+def run_tigre_style(args, cfg):
+    """One OS-SART subset (blocksize angles) of the workload with the TIGRE-style baseline kernels
+    (csrc/tigre_style.cu: 9x9x9 hardware-trilinear texture Ax, 16x32x8z texture Atb) beside the product kernels:
+    ms per launch, error of each against the float64 oracle on two angles, and the volume time the Ax / Atb
+    kernels alone would add up to (1 + niter Ax passes, niter Atb passes)."""
+    import ctypes
+    import torch
+    from oracle import cpu_oracle
+    from physics_arx_b200 import _lib
+    from physics_arx_b200.phantom import lung_phantom
+    from physics_arx_b200.projector import Plan, _ptr, _stream
+    lib = _lib.load()
+    torch.cuda.set_device(0)
+    geo, angles_all = cfg["geo"], cfg["angles"]
+    b = cfg["blocksize"]
+    angles = angles_all[np.linspace(0, len(angles_all) - 1, b).astype(int)]       # one subset's worth, spread
+    plan = Plan(geo, angles)
+    vol_np = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    vol = torch.from_numpy(vol_np).cuda()
+    res = plan.pack(vol)
+    ts = ctypes.c_void_p()
+    _lib.check(lib.pax_ts_create(plan._h, ctypes.byref(ts)), "pax_ts_create")
+    proj_ts = torch.empty((b, plan.nv, plan.nu), dtype=torch.float32, device="cuda")
+    back_ts = torch.empty((plan.nz, plan.ny, plan.nx), dtype=torch.float32, device="cuda")
+    back = plan.new_volume()
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 1)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(max(args.steps, 1)):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / max(args.steps, 1)
+
+    _lib.check(lib.pax_ts_set_volume(ts, _ptr(vol), _stream()), "pax_ts_set_volume")
+    t_up = timed(lambda: _lib.check(lib.pax_ts_set_volume(ts, _ptr(vol), _stream()), "pax_ts_set_volume"))
+    t_ax_ts = timed(lambda: _lib.check(lib.pax_ts_ax(ts, 0, b, _ptr(proj_ts), _stream()), "pax_ts_ax"))
+    proj = plan.ax(res)
+    t_ax = timed(lambda: plan.ax(res, out=proj))
+    t_atb_ts = timed(lambda: _lib.check(lib.pax_ts_atb(ts, _ptr(proj), 0, b, _ptr(back_ts), _stream()), "pax_ts_atb"))
+    t_atb = timed(lambda: plan.atb(proj, 0, b, back, _lib.PAX_ATB_STORE))
+    # accuracy of both against the float64 oracle (two angles)
+    pick = [0, b // 2]
+    ref = cpu_oracle.ax(vol_np, geo, angles[pick])
+
+    def rel(a, r):
+        return float(np.linalg.norm(a.astype(np.float64) - r) / np.linalg.norm(r))
+
+    err_ts = rel(proj_ts[pick].cpu().numpy(), ref)
+    err = rel(proj[pick].cpu().numpy(), ref)
+    back_ref = cpu_oracle.atb(proj.cpu().numpy(), geo, angles)
+    err_atb_ts = rel(back_ts.cpu().numpy(), back_ref)
+    err_atb = rel(plan.unpack(back).cpu().numpy(), back_ref)
+    lib.pax_ts_destroy(ts)
+    nsub = -(-len(angles_all) // b)
+    niter = cfg["niter"]
+    vol_ts = (1 + niter) * nsub * t_ax_ts + niter * nsub * (t_atb_ts + t_up)
+    vol_us = (1 + niter) * nsub * t_ax + niter * nsub * t_atb
+    line = {"impl": "tigre_style", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "config": describe(cfg, 1),
+            "value": 1e3 / vol_ts, "ms_per_step": vol_ts, "higher_is_better": True, "dtype": "f32",
+            "data": "synthetic", "steps": args.steps, "warmup": args.warmup,
+            "what": f"Ax and Atb kernels only, one {b}-angle subset timed and multiplied out to 1+{niter} Ax and "
+                    f"{niter} Atb passes over {nsub} subsets; TIGRE itself also moves every array over PCIe per "
+                    "call (SURVEY F8), which is not charged here",
+            "tigre_style": {"ax_ms_per_subset": t_ax_ts, "atb_ms_per_subset": t_atb_ts,
+                            "volume_texture_upload_ms": t_up, "ax_rel_l2_vs_oracle": err_ts,
+                            "atb_rel_l2_vs_oracle": err_atb_ts, "kernels_only_ms_per_volume": vol_ts},
+            "ours": {"ax_ms_per_subset": t_ax, "atb_ms_per_subset": t_atb, "ax_rel_l2_vs_oracle": err,
+                     "atb_rel_l2_vs_oracle": err_atb, "kernels_only_ms_per_volume": vol_us,
+                     "projector": plan.projector},
+            "speedup_kernels_only": vol_ts / vol_us}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------- multi-GPU parity (untimed)
 def parity_vs_single_gpu(group, rank, world):
     """A small case (tests/test_multigpu.py's geometry) run sharded over the group -- once with the default
@@ -241,7 +320,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="C2", choices=["C1", "C2"])
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "tigre_style"],
+                    help="ours: the product path; reference: the float64 CPU oracle (the driver's baseline arm); "
+                         "tigre_style: the recalled TIGRE launch shapes on this GPU (csrc/tigre_style.cu), one subset")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the untimed C1/C4/C5 and multi-GPU parity legs")
@@ -254,6 +335,10 @@ def main():
     cfg = get_config(args.config)
     if args.impl == "reference":
         run_reference(args, cfg, rank)
+        return
+    if args.impl == "tigre_style":
+        if rank == 0:
+            run_tigre_style(args, cfg)
         return
     if args.warmup < 3:
         print("warning: fewer than 3 warm-up steps", file=sys.stderr)

@@ -215,6 +215,26 @@ int pax_rescale_intensity(float *x, size_t n, const float *minmax_dev, double ou
 int pax_plahe(const float *src, int nz, int ny, int nx, int radius, float alpha, float beta,
               const float *minmax_dev, float *dst, void *stream);
 
+/* Output side.
+ * pax_resize: skimage.transform.resize(order 0 | 1, preserve_range, no anti-aliasing) of a 3-D array, as the
+ * reference's packing script calls it (preprocess/prep_test_data_pseudo_cbct_3D.py:23-36): pixel-centre aligned
+ * coordinates, 'mirror' boundary, double arithmetic.  src (s0,s1,s2) -> dst (d0,d1,d2), both device, C order.
+ * pax_pair_sums: out6 = { n, sum a, sum b, sum a^2, sum b^2, sum a b } in double -- what RMSE / CC / UQI of two
+ * volumes need (the Quameasopts of ossart, pCT_CBCT_Reconstruction.py:99-103). */
+int pax_resize(const float *src, int s0, int s1, int s2, float *dst, int d0, int d1, int d2, int order, void *stream);
+int pax_pair_sums(const float *a, const float *b, size_t n, double *out6_dev, void *stream);
+
+/* "TIGRE-style" baseline kernels -- benchmark reference only, not on the product path (csrc/tigre_style.cu): the
+ * launch shapes of the toolbox the reference calls (9x9x9 hardware-trilinear texture Ax, 16x32x8z constant-memory
+ * texture Atb), compiled for sm_100a as the kernels to beat.  Plain (Z,Y,X) device volumes in and out.  The handle
+ * owns a 3-D and a layered CUDA array (these entry points DO allocate, unlike the product's). */
+typedef struct PaxTs PaxTs;
+int pax_ts_create(const PaxPlan *plan, PaxTs **out);
+int pax_ts_destroy(PaxTs *ts);
+int pax_ts_set_volume(PaxTs *ts, const float *vol_zyx, void *stream);
+int pax_ts_ax(PaxTs *ts, int first, int count, float *proj_out, void *stream);
+int pax_ts_atb(PaxTs *ts, const float *proj, int first, int count, float *vol_zyx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,14 @@ SYMBOLS = [
     ("pax_minmax", ctypes.c_int, [_VP, ctypes.c_size_t, _VP, _VP]),
     ("pax_rescale_intensity", ctypes.c_int, [_VP, ctypes.c_size_t, _VP, ctypes.c_double, ctypes.c_double,
                                              _VP]),
+    ("pax_ts_create", ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_void_p)]),
+    ("pax_ts_destroy", ctypes.c_int, [_VP]),
+    ("pax_ts_set_volume", ctypes.c_int, [_VP, _VP, _VP]),
+    ("pax_ts_ax", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    ("pax_ts_atb", ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP]),
+    ("pax_resize", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, _VP]),
+    ("pax_pair_sums", ctypes.c_int, [_VP, _VP, ctypes.c_size_t, _VP, _VP]),
     ("pax_plahe", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_float, ctypes.c_float, _VP, _VP, _VP]),
     ("pax_ctnoise", ctypes.c_int, [_VP, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_uint64,

@@ -309,7 +309,8 @@ def ossart(proj, geo, angles, niter, **kwargs):
     """OS-SART with TIGRE's signature and defaults (A.6).
 
     kwargs: blocksize=20, lmbda=1, lmbda_red=0.99, OrderStrategy=None, init=None,
-    noneg=True, verbose=False, computel2=False, gpuids=None; build extras: w_variant,
+    noneg=True, verbose=False, computel2=False, Quameasopts=None (a subset of RMSE / CC / MSSIM / UQI, measured
+    between the iterate before and after every iteration: utilities/quality.py), gpuids=None; build extras: w_variant,
     v_variant, group / distributed / shard (sharding over a torch.distributed group; dist.py),
     fused_update (the multi-GPU update as one kernel over symmetric memory; include/pax.h).
     Returns the (Z,Y,X) float32 volume (NumPy in -> NumPy out); with computel2 also the
@@ -324,8 +325,10 @@ def ossart(proj, geo, angles, niter, **kwargs):
     verbose = kwargs.pop("verbose", False)
     computel2 = kwargs.pop("computel2", False)
     gpuids = kwargs.pop("gpuids", None)
-    if kwargs.pop("Quameasopts", None) is not None:
-        raise NotImplementedError("Quameasopts is not on this path (commented out in the reference, :103)")
+    quameas = kwargs.pop("Quameasopts", None)
+    if quameas is not None:
+        from ..utilities.quality import check_opts
+        quameas = check_opts(quameas)
     state_kw = {k: kwargs.pop(k) for k in ("w_variant", "v_variant", "group", "distributed", "shard",
                                            "fused_update") if k in kwargs}
     if kwargs:
@@ -348,6 +351,8 @@ def ossart(proj, geo, angles, niter, **kwargs):
             raise ValueError(f"proj shape {tuple(proj.shape)} != (N, *geo.nDetector) {(nang, nv, nu)}")
         if isinstance(init, str):
             raise NotImplementedError(f"init={init!r} is not on this path (reference uses the default, zeros)")
+        if quameas is not None:
+            raise NotImplementedError("Quameasopts with several devices in one process: pass a single device")
         from ..multidev import MultiDevice
         md = MultiDevice(geo, angles, devs, blocksize=blocksize, OrderStrategy=order)
         x0 = None if init is None else _to_cuda(init, md.devices[0], "init")[0]
@@ -371,11 +376,15 @@ def ossart(proj, geo, angles, niter, **kwargs):
         x0, _ = _to_cuda(init, b.device, "init")
         x = p.pack(x0, out=st.new_iterate())
     lam = lmbda
-    l2 = []
+    l2, lq = [], []
     for it in range(int(niter)):
         if computel2:
             st.sumsq.zero_()
+        prev = p.unpack(x) if quameas is not None else None      # Measure_Quality(res_prev, res) per iteration
         st.iteration(x, lam, noneg, computel2)
+        if quameas is not None:
+            from ..utilities.quality import Measure_Quality
+            lq.append(Measure_Quality(prev, p.unpack(x), quameas))
         if computel2:
             ss = st.sumsq.clone()
             if st.world > 1:
@@ -387,7 +396,8 @@ def ossart(proj, geo, angles, niter, **kwargs):
     out = p.unpack(x)
     p.check_fault()                    # the fan-plane projector's self-check (csrc/ax_fan.cu)
     out = out.cpu().numpy() if was_np else out
-    return (out, np.array(l2)) if computel2 else out
+    extra = ([np.array(l2)] if computel2 else []) + ([np.array(lq).T] if quameas is not None else [])
+    return (out, *extra) if extra else out        # TIGRE: (res, l2) / (res, quality[measure, iteration])
 
 
 OS_SART = ossart

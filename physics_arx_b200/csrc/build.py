@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["plan.cu", "ax.cu", "ax_fan.cu", "atb.cu", "image_ops.cu"]
+SOURCES = ["plan.cu", "ax.cu", "ax_fan.cu", "atb.cu", "image_ops.cu", "tigre_style.cu"]
 HEADERS = ["pax_internal.h", os.path.join(ROOT, "include", "pax.h")]
 OUT = os.path.join(HERE, "libpax.so")
 

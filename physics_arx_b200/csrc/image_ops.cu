@@ -249,3 +249,103 @@ extern "C" int pax_plahe(const float *src, int nz, int ny, int nx, int radius, f
     PAX_CHECK_CUDA(cudaGetLastError());
     return PAX_OK;
 }
+
+// ------------------------------------------------------------------ resize (output side)
+// skimage.transform.resize(img, shape, order=0|1, preserve_range=True, anti_aliasing=False) as the reference's
+// packing script calls it (preprocess/prep_test_data_pseudo_cbct_3D.py:23-36; scikit-image 0.17.2 per
+// environment.yaml:124): for a 3-D array that is scipy.ndimage.map_coordinates at the pixel-centre aligned
+// coordinates  c_d = (in_d / out_d) (o_d + 1/2) - 1/2  with mode 'mirror' (d c b | a b c d | c b a) -- order 0
+// takes the sample at floor(c + 1/2), order 1 interpolates linearly.  Coordinates in double, like scipy.
+__device__ __forceinline__ double rs_mirror(double c, int n)
+{
+    if (n <= 1) return 0.0;
+    const double len = (double)(n - 1);
+    if (c < 0.0) {                             // scipy's map_coordinate(), NI_EXTEND_MIRROR
+        const double sz2 = 2.0 * len;
+        c = sz2 * (double)(long long)(-c / sz2) + c;
+        c = c <= -len ? c + sz2 : -c;
+    } else if (c > len) {
+        const double sz2 = 2.0 * len;
+        c -= sz2 * (double)(long long)(c / sz2);
+        if (c > len) c = sz2 - c;
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(256) k_resize(const float *__restrict__ src, int s0, int s1, int s2,
+                                                float *__restrict__ dst, int d0, int d1, int d2, int order)
+{
+    const size_t n = (size_t)d0 * d1 * d2;
+    const double f0 = (double)s0 / d0, f1 = (double)s1 / d1, f2 = (double)s2 / d2;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int o2 = (int)(e % d2), o1 = (int)((e / d2) % d1), o0 = (int)(e / ((size_t)d1 * d2));
+        const double c0 = rs_mirror(f0 * (o0 + 0.5) - 0.5, s0), c1 = rs_mirror(f1 * (o1 + 0.5) - 0.5, s1),
+                     c2 = rs_mirror(f2 * (o2 + 0.5) - 0.5, s2);
+        if (order == 0) {
+            const int i0 = min(max((int)floor(c0 + 0.5), 0), s0 - 1), i1 = min(max((int)floor(c1 + 0.5), 0), s1 - 1),
+                      i2 = min(max((int)floor(c2 + 0.5), 0), s2 - 1);
+            dst[e] = __ldg(src + ((size_t)i0 * s1 + i1) * s2 + i2);
+        } else {
+            const int i0 = min((int)floor(c0), max(s0 - 2, 0)), i1 = min((int)floor(c1), max(s1 - 2, 0)),
+                      i2 = min((int)floor(c2), max(s2 - 2, 0));
+            const double t0 = c0 - i0, t1 = c1 - i1, t2 = c2 - i2;
+            const int j0 = min(i0 + 1, s0 - 1), j1 = min(i1 + 1, s1 - 1), j2 = min(i2 + 1, s2 - 1);
+            double acc = 0.0;                  // scipy sums the 2^3 taps with the products of the 1-D weights
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b)
+                    for (int c = 0; c < 2; ++c) {
+                        const double w = (a ? t0 : 1.0 - t0) * (b ? t1 : 1.0 - t1) * (c ? t2 : 1.0 - t2);
+                        acc += w * (double)__ldg(src + ((size_t)(a ? j0 : i0) * s1 + (b ? j1 : i1)) * s2 + (c ? j2 : i2));
+                    }
+            dst[e] = (float)acc;
+        }
+    }
+}
+
+extern "C" int pax_resize(const float *src, int s0, int s1, int s2, float *dst, int d0, int d1, int d2, int order,
+                          void *stream)
+{
+    PAX_REQUIRE(src && dst && src != dst, "pax_resize: NULL or aliased argument");
+    PAX_REQUIRE(s0 >= 1 && s1 >= 1 && s2 >= 1 && d0 >= 1 && d1 >= 1 && d2 >= 1, "pax_resize: empty array");
+    PAX_REQUIRE(order == 0 || order == 1, "pax_resize: order %d (0 = nearest, 1 = linear)", order);
+    const size_t n = (size_t)d0 * d1 * d2;
+    const int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
+    k_resize<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, s0, s1, s2, dst, d0, d1, d2, order);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
+// ------------------------------------------------------ image quality measures (Quameasopts)
+// The sums TIGRE's Measure_Quality needs for RMSE, CC and UQI of two volumes, in one pass, in double:
+// out[0..5] += { n, sum a, sum b, sum a^2, sum b^2, sum a b }.  (MSSIM is a windowed measure: quality.py.)
+__global__ void __launch_bounds__(256) k_pair_sums(const float *__restrict__ a, const float *__restrict__ b,
+                                                   size_t n, double *__restrict__ out)
+{
+    double s[5] = {0, 0, 0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double x = a[i], y = b[i];
+        s[0] += x; s[1] += y; s[2] += x * x; s[3] += y * y; s[4] += x * y;
+    }
+    __shared__ double sm[5][8];
+    for (int k = 0; k < 5; ++k) {
+        for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+        if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[threadIdx.x][w];
+        atomicAdd(out + 1 + threadIdx.x, t);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (double)n);
+}
+
+extern "C" int pax_pair_sums(const float *a, const float *b, size_t n, double *out6_dev, void *stream)
+{
+    PAX_REQUIRE(a && b && out6_dev && n > 0, "pax_pair_sums: bad argument");
+    PAX_CHECK_CUDA(cudaMemsetAsync(out6_dev, 0, 6 * sizeof(double), (cudaStream_t)stream));
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    k_pair_sums<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, b, n, out6_dev);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
