@@ -454,12 +454,25 @@ def main():
         avg_ms = float(np.mean(ax_ms)) if ax_ms else float("nan")
         alg_bytes = 4.0 * nvox + 8.0 * avg_count * npix
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if ax_ms else 0.0
-        traffic = None
+        traffic, wavefronts = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
-                f"{cfg['name']}_ax_residual_bytes_per_launch_{pipe.plan.projector}")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = prof.get(f"{cfg['name']}_ax_residual_bytes_per_launch_{pipe.plan.projector}")
+            wavefronts = prof.get(f"{cfg['name']}_ax_residual_l1_wavefronts_per_launch_{pipe.plan.projector}")
         except Exception:
             pass
+        # the honest bound of this kernel: the L1 data pipe (shared-memory tables + global-load wavefronts), one
+        # wavefront per clock and SM; wavefronts per launch from the committed ncu capture (full 20-angle launch)
+        sm_clock = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        l1_peak = 148.0 * sm_clock
+        l1 = None
+        if wavefronts and ax_ms and world == 1:
+            full = [m for m, c in zip(ax_ms, ax_counts) if c == cfg["blocksize"]] or ax_ms
+            ach = wavefronts / (float(np.mean(full)) * 1e-3)
+            l1 = {"bound": "l1_data_pipe", "achieved": ach / 1e9, "peak": l1_peak / 1e9, "unit": "Gwavefronts/s",
+                  "frac": ach / l1_peak, "wavefronts_per_launch": wavefronts,
+                  "peak_source": "1 wavefront per clock and SM x 148 SMs x the SM clock sampled under load",
+                  "source": "profiles/r2_ncu_fan.json (l1tex__data_pipe_lsu_wavefronts)"}
         ax_share = float(sum(ax_ms)) / float(t[0].item()) if ax_ms else None
         samples_resid = samples_per_pass * cfg["niter"] * args.steps     # rank 0's residual passes
         line = {
@@ -480,8 +493,9 @@ def main():
                                     "k_ax<1,RESIDUAL,32> (ray-march projector, csrc/ax.cu)"),
                          "peak_source": peak_src, "avg_launch_ms": avg_ms,
                          "alg_bytes_per_launch": alg_bytes, "share_of_step": ax_share,
-                         "note": "issue- and latency-bound gather + prefix sums, not HBM-bound: see "
-                                 "ax_gsamples_per_s and profiles/"},
+                         "note": "a gather plus prefix sums bound by per-warp latency and the L1 data pipe, not by "
+                                 "HBM: see roofline_l1, ax_gsamples_per_s and profiles/"},
+            "roofline_l1": l1,
             "gpu_launches": launches,
             "subset_step_ms": dict(ax=float(np.mean(ax_ms)) if ax_ms else None, **phases,
                                    total=(ms / args.steps) / max(cfg["niter"] * len(pipe.st.blocks), 1),

@@ -591,7 +591,6 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     switch (p->fan_cw * 10000 + p->fan_warps * 100 + p->fan_minb) {
     case 80404: return fan_launch_mode<8, 4, 4>(a, mode, count, st);          // the default
     case 80802: return fan_launch_mode<8, 8, 2>(a, mode, count, st);
-    case 40404: return fan_launch_mode<4, 4, 4>(a, mode, count, st);
     default: break;
     }
     return pax_set_error(PAX_ERR_INVALID, "pax_ax: unsupported fan configuration CW=%d warps=%d minb=%d", p->fan_cw,
@@ -612,14 +611,14 @@ int pax_fan_configure(PaxPlan *p)
     }
     const char *e;
     int cw = 8, nw = 4;
-    if ((e = getenv("PAX_FAN_CW")) && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16)) cw = atoi(e);   // tuning hooks
+    if ((e = getenv("PAX_FAN_CW")) && atoi(e) == 8) cw = atoi(e);                                   // tuning hooks
     if ((e = getenv("PAX_FAN_NW")) && (atoi(e) == 4 || atoi(e) == 8)) nw = atoi(e);
     int minb = 16 / nw;
     if ((e = getenv("PAX_FAN_MINB")) && atoi(e) >= 1) minb = atoi(e);
     p->fan_minb = minb;
     // a single row must fit the 32 lanes (128 slices) of a pass over one epoch, with room to spare for its
     // neighbours: halve the epoch until its z travel is at most 64 slices
-    int ep = 128;
+    int ep = 160;
     if ((e = getenv("PAX_FAN_EPOCH")) && atoi(e) >= cw && atoi(e) <= FAN_EPMAX) ep = atoi(e) / cw * cw;
     if (ep > 32 * cw) ep = 32 * cw;                             // at most 32 windows per epoch (rtab)
     while (ep >= cw && ep * slope > 64.0) ep /= 2;
