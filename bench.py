@@ -234,10 +234,20 @@ def run_tigre_style(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def collective_name(st):
+    if st.scheme == "gather":
+        return ("residual all-gather + row-owned backprojection/update + row broadcast (multimem kernels), "
+                + st.gsym["kind"])
+    if st.fused is not None:
+        return "fused reduce + update + broadcast kernel over " + st.fused["kind"]
+    return "NCCL all-reduce + local update kernel"
+
+
 # ------------------------------------------------------------- multi-GPU parity (untimed)
 def parity_vs_single_gpu(group, rank, world):
-    """A small case (tests/test_multigpu.py's geometry) run sharded over the group -- once with the default
-    collective, once with the fused reduce+update kernel forced -- against the same case on rank 0 alone."""
+    """A small case (tests/test_multigpu.py's geometry) run sharded over the group -- once as a caller gets it
+    (the gather scheme), once with the reduce scheme and its fused reduce+update+broadcast kernel forced --
+    against the same case on rank 0 alone."""
     import torch
     import torch.distributed as dist
     from physics_arx_b200.phantom import artifact_volume, lung_phantom, make_geometry
@@ -249,11 +259,11 @@ def parity_vs_single_gpu(group, rank, world):
     kw = dict(niter=3, blocksize=5, I0=1e8, sigma=4.0, scatter_scale=0.5, seed=3)
     single = SCBCTPipeline(geo, angles, **kw).run_device(ct, art).clone() if rank == 0 else None
     out = {}
-    for name, fused in (("default", None), ("fused", True)):
+    for name, fused, shard in (("default", None, "auto"), ("fused_reduce", True, "grid")):
         try:
-            pipe = SCBCTPipeline(geo, angles, group=group, fused_update=fused, **kw)
+            pipe = SCBCTPipeline(geo, angles, group=group, fused_update=fused, shard=shard, **kw)
             got = pipe.run_device(ct, art).clone()
-            coll = "nccl all-reduce" if pipe.st.fused is None else "fused kernel, " + pipe.st.fused["kind"]
+            coll = collective_name(pipe.st)
             ref = got.clone()
             dist.broadcast(ref, src=0, group=group)
             same = torch.tensor([1 if torch.equal(got, ref) else 0], dtype=torch.int32, device="cuda")
@@ -484,8 +494,7 @@ def main():
                 "grid": list(pipe.st.grid), "mode": pipe.st.shard,
                 "meaning": "ranks as (angle groups) x (detector bands): the angles of every subset interleaved over "
                            "the groups, each group splitting the detector into bands",
-                "collective": ("fused reduce + update + broadcast kernel over " + pipe.st.fused["kind"]
-                               if pipe.st.fused is not None else "NCCL all-reduce + local update kernel")}),
+                "scheme": pipe.st.scheme, "collective": collective_name(pipe.st)}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": ("k_ax_fan<8,4,4,RESIDUAL> (event-driven fan-plane projector, csrc/ax_fan.cu)"

@@ -93,6 +93,9 @@ typedef struct PaxAtbEpilogue {
     int32_t noneg;
     float lambda;
     const float *inv_v;             /* device (Y,X): 1/V_s, 0 where V_s == 0 */
+    int32_t row_part, row_parts;    /* row_parts > 1: only the volume rows y = row_part (mod row_parts) are
+                                       computed and written (multi-GPU: every rank backprojects ALL angles of the
+                                       subset into its own rows); 0 / 0 or 0 / 1: every row */
 } PaxAtbEpilogue;
 
 int pax_version(void);
@@ -166,6 +169,15 @@ int pax_sart_update(const PaxPlan *plan, float *x_res, const float *upd_res, con
  * symmetric buffers (x_mc, upd_mc: NVSwitch multimem.ld_reduce / multimem.st) or the `world` peer pointers of
  * each (x_peers, upd_peers: host arrays of device addresses).  The caller synchronises the ranks before (all
  * partial updates complete) and after (all slices landed); every rank ends with bit-identical x. */
+/* Multi-GPU plumbing over symmetric (peer-mapped) buffers: copy `n_chunks` chunks of `chunk_bytes` (a multiple of
+ * 16) -- chunk numbers first_chunk, first_chunk + chunk_stride, ... -- from this rank's buffer to the same place
+ * in EVERY rank's buffer, either through the buffer's multicast address (dst_mc: one multimem.st per 16 bytes, the
+ * NVSwitch replicates) or through the `world` peer pointers (dst_peers).  Used to all-gather the residual
+ * projections of a subset (chunk = one projection) and to broadcast the volume rows a rank has updated (chunk =
+ * one row of the resident volume, stride = world).  The caller synchronises the ranks around it. */
+int pax_bcast_chunks(const void *src_local, void *dst_mc, const uint64_t *dst_peers, int world, size_t chunk_bytes,
+                     long first_chunk, long chunk_stride, long n_chunks, void *stream);
+
 int pax_sart_update_fused(const PaxPlan *plan, float *x_local, float *x_mc, const float *upd_mc,
                           const uint64_t *x_peers, const uint64_t *upd_peers, int rank, int world,
                           const float *inv_v, float lambda, int noneg, void *stream);

@@ -36,7 +36,7 @@ class PaxAxEpilogue(ctypes.Structure):
 
 class PaxAtbEpilogue(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_int32), ("noneg", ctypes.c_int32), ("lambda_", ctypes.c_float),
-                ("inv_v", ctypes.c_void_p)]
+                ("inv_v", ctypes.c_void_p), ("row_part", ctypes.c_int32), ("row_parts", ctypes.c_int32)]
 
 
 # every symbol include/pax.h declares: (name, restype, argtypes)
@@ -66,6 +66,8 @@ SYMBOLS = [
     ("pax_atb", ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
                                ctypes.POINTER(PaxAtbEpilogue), _VP]),
     ("pax_sart_update", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_float, ctypes.c_int, _VP]),
+    ("pax_bcast_chunks", ctypes.c_int, [_VP, _VP, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_size_t,
+                                        ctypes.c_long, ctypes.c_long, ctypes.c_long, _VP]),
     ("pax_sart_update_fused", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_uint64),
                                              ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, _VP,
                                              ctypes.c_float, ctypes.c_int, _VP]),

@@ -40,6 +40,11 @@ def _cur_stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def os_environ(name):
+    import os
+    return os.environ.get(name, "")
+
+
 def _dist_info(group, distributed):
     import torch.distributed as dist
     if distributed is False or not (dist.is_available() and dist.is_initialized()):
@@ -69,9 +74,26 @@ class OSSARTState:
         dev = proj.device if proj is not None else torch.device(
             "cuda", torch.cuda.current_device() if device is None else int(device))
         nv_full, nu = (int(v) for v in geo.nDetector)
+        self.v_variant = v_variant
+        self.angles = angles
+        # Multi-GPU scheme.  "gather" (default where symmetric memory works): the angles of every subset in
+        # consecutive shares, every rank's residual projections broadcast into every rank's copy of the subset's
+        # residual set, every rank backprojects ALL of them into its own rows of the volume (with the SART update
+        # in the epilogue, as on one GPU) and broadcasts those rows.  63 MB of residuals cross the fabric per C2
+        # subset instead of a 144 MB partial update per rank, there is no reduction and no separate update pass,
+        # and the result is the single-GPU arithmetic voxel for voxel.  "reduce": every rank backprojects its own
+        # residuals into a partial update of the whole volume and the partial updates are summed (fused
+        # reduce + update + broadcast kernel, or NCCL all-reduce + update); used for explicit shard= modes.
+        self.scheme, self.gsym, self.plan_full = "reduce", None, None
+        import os
+        if (self.world > 1 and shard == "auto" and fused_update is not False
+                and os.environ.get("PAX_MGPU", "gather") == "gather" and os.environ.get("PAX_FUSED_UPDATE", "") != "0"):
+            self._setup_gather(dev)
         # the ranks form an A x R grid: the angles of every subset over A groups, the detector over R bands
         # (of columns, or of rows with shard='rows')
         self.grid = choose_shard(self.blocks, self.world, shard) if self.world > 1 else (1, 1)
+        if self.scheme == "gather":
+            self.grid = (self.world, 1)
         A, R = self.grid
         self.axis = band_axis(shard)
         self.shard = "angles" if R == 1 else (self.axis if A == 1 else "grid")
@@ -81,7 +103,7 @@ class OSSARTState:
             self.v0, self.v1 = shard_rows(nv_full, rr, R)
         elif R > 1:
             self.u0, self.u1 = shard_rows(nu, rr, R, align=8)     # whole 32-byte sectors of a projection row
-        local, self.ranges = shard_blocks(self.blocks, ra, A)
+        local, self.ranges = shard_blocks(self.blocks, ra, A, contiguous=self.scheme == "gather")
         # a rank may own no angle at all (n < A): keep one dummy angle so a plan exists
         plan_idx = local if len(local) else np.array([0])
         sub_geo = subset_geometry(geo, plan_idx, n)
@@ -123,35 +145,98 @@ class OSSARTState:
         else:
             sel = proj[torch.as_tensor(local, device=dev, dtype=torch.long)] if n_own else proj[:0]
             self.b = sel[:, self.v0:self.v1, self.u0:self.u1].contiguous()
-        # V_s (A.5): a sum over the subset's angles, so partial sums all-reduce exactly
         p = self.plan
-        V = torch.zeros((len(self.blocks), p.ny, p.nx), dtype=torch.float32, device=dev)
-        if v_variant == "A":
-            for s, (first, count) in enumerate(self.ranges):
-                if count:
-                    p.compute_v(first, count, out=V[s])
-            if self.tiles is not None:      # every rank of an angle group computed the whole detector's map
-                V /= self.tiles[1]
-        elif v_variant == "B":
-            V.copy_(torch.from_numpy(_v_variant_b(geo, angles, self.blocks)).to(dev))
-            if self.world > 1:
-                V /= self.world
-        else:
-            raise ValueError(f"unknown V variant {v_variant!r}")
-        if self.world > 1:
-            dist.all_reduce(V, group=self.group)
-        self.inv_v = torch.where(V > 1e-12, 1.0 / V, torch.zeros_like(V)).contiguous()
+        self.inv_v = self.compute_inv_v()
         self.max_count = max((c for _, c in self.ranges), default=0)
         # (zeros: with a share of the column tiles the other ranks' columns are never written and must read 0)
         self.resid = torch.zeros((max(self.max_count, 1), p.nv, p.nu), dtype=torch.float32, device=dev)
-        self.upd = p.new_volume() if self.world > 1 else None
+        self.upd = p.new_volume() if (self.world > 1 and self.scheme == "reduce") else None
         self.fused = None              # symmetric-memory state of the fused reduce + update + broadcast
-        if self.world > 1 and fused_update is not False:
+        if self.world > 1 and fused_update is not False and self.scheme == "reduce":
             self._setup_fused(dev, required=fused_update is True)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.launches = 0              # kernels of libpax launched by subset_step (bench claim)
         self.kernel_events = None      # set to [] to record CUDA events around the Ax kernel
         self.phase_events = {}         # ... and around the other phases of a subset step (bench breakdown)
+
+    def compute_inv_v(self):
+        """1 / V_s per subset (A.5).  V_s is a sum over the subset's angles: in the "reduce" scheme the ranks'
+        partial sums are all-reduced; in the "gather" scheme every rank evaluates the whole subset itself."""
+        import torch.distributed as dist
+        p = self.plan
+        dev = p.device
+        V = torch.zeros((len(self.blocks), p.ny, p.nx), dtype=torch.float32, device=dev)
+        if self.v_variant == "A":
+            if self.scheme == "gather":
+                for s, (gfirst, glen) in enumerate(self.gsym["granges"]):
+                    self.plan_full.compute_v(gfirst, glen, out=V[s])
+            else:
+                for s, (first, count) in enumerate(self.ranges):
+                    if count:
+                        p.compute_v(first, count, out=V[s])
+                if self.tiles is not None:      # every rank of an angle group computed the whole detector's map
+                    V /= self.tiles[1]
+        elif self.v_variant == "B":
+            V.copy_(torch.from_numpy(_v_variant_b(self.geo, self.angles, self.blocks)).to(dev))
+            if self.world > 1 and self.scheme == "reduce":
+                V /= self.world
+        else:
+            raise ValueError(f"unknown V variant {self.v_variant!r}")
+        if self.world > 1 and self.scheme == "reduce":
+            dist.all_reduce(V, group=self.group)
+        return torch.where(V > 1e-12, 1.0 / V, torch.zeros_like(V)).contiguous()
+
+    # --------------------------------------------- gather scheme (csrc/plan.cu: pax_bcast_chunks; atb.cu row shares)
+    def _setup_gather(self, dev):
+        """Symmetric buffers for the iterate and for one subset's residual projections, plus a plan over ALL
+        angles in subset order (the backprojection of a subset runs over every rank's residuals).  Leaves
+        scheme == "reduce" when symmetric memory cannot be set up on every rank."""
+        import ctypes
+        import torch.distributed as dist
+        g = self.group if self.group is not None else dist.group.WORLD
+        if self.world > _lib.PAX_MAX_PEERS:
+            return
+        ok, st = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            if dist.get_backend(g) != "nccl":
+                raise RuntimeError("the gather scheme needs the nccl backend")
+            order = np.concatenate([np.asarray(b) for b in self.blocks])
+            with torch.cuda.device(dev):
+                full = Plan(subset_geometry(self.geo, order, self.n), self.angles[order], device=dev.index)
+                full.w_geo = self.geo
+                maxb = max(len(b) for b in self.blocks)
+                npix = full.nv * full.nu
+                if (npix * 4) % 16 or (full.nxp_nzp_bytes % 16):
+                    raise RuntimeError("projection / volume rows are not multiples of 16 bytes")
+                x = symm.empty(full.vol_elems, dtype=torch.float32, device=dev)
+                r = symm.empty(maxb * npix, dtype=torch.float32, device=dev)
+                x.zero_()
+                r.zero_()
+                hx, hr = symm.rendezvous(x, g), symm.rendezvous(r, g)
+            mc_x = int(getattr(hx, "multicast_ptr", 0) or 0)
+            mc_r = int(getattr(hr, "multicast_ptr", 0) or 0)
+            use_mc = bool(mc_x and mc_r) and os_environ("PAX_FUSED_UPDATE") != "p2p"
+            arr = ctypes.c_uint64 * self.world
+            pos, granges = 0, []
+            for b in self.blocks:
+                granges.append((pos, len(b)))
+                pos += len(b)
+            st = dict(x=x, r=r.view(maxb, full.nv, full.nu), hx=hx, hr=hr, mc_x=mc_x if use_mc else 0,
+                      mc_r=mc_r if use_mc else 0, x_peers=arr(*[int(v) for v in hx.buffer_ptrs]),
+                      r_peers=arr(*[int(v) for v in hr.buffer_ptrs]), granges=granges,
+                      kind="multicast" if use_mc else "peer pointers", npix=npix)
+        except Exception as e:                     # noqa: BLE001 -- any failure means "not available here"
+            ok = 0
+            self.gather_error = repr(e)
+        try:                                       # every rank must take the same path
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=g)
+            ok = int(flag.item())
+        except Exception:                          # noqa: BLE001
+            ok = 0
+        if ok:
+            self.scheme, self.gsym, self.plan_full = "gather", st, full
 
     # ------------------------------------------------- fused collective (csrc/plan.cu: k_sart_update_fused)
     def _setup_fused(self, dev, required=False):
@@ -214,6 +299,9 @@ class OSSARTState:
     def new_iterate(self):
         """Zeroed resident volume for x.  With the fused collective it is THE symmetric buffer the peers
         write into (one per OSSARTState; a second call returns the same tensor, zeroed)."""
+        if self.scheme == "gather":
+            self.gsym["x"].zero_()
+            return self.gsym["x"]
         if self.fused is not None:
             self.fused["x"].zero_()
             return self.fused["x"]
@@ -235,6 +323,8 @@ class OSSARTState:
         p = self.plan
         first, count = self.ranges[s]
         ss = self.sumsq if computel2 else None
+        if self.scheme == "gather":
+            return self._subset_step_gather(x_res, s, lam, noneg, ss)
         if count:
             ev = None
             if self.kernel_events is not None:     # bench: time the dominant kernel in place
@@ -280,6 +370,44 @@ class OSSARTState:
         self._timed("update", lambda: (dist.all_reduce(self.upd, group=self.group),
                                        p.sart_update(x_res, self.upd, self.inv_v[s], lam, noneg)))
         self.launches += 1
+
+    def _subset_step_gather(self, x_res, s, lam, noneg, ss):
+        p, f = self.plan, self.gsym
+        if x_res.data_ptr() != f["x"].data_ptr():
+            raise ValueError("the gather scheme iterates on the symmetric buffer new_iterate() returns")
+        first, count = self.ranges[s]
+        gfirst, glen = f["granges"][s]
+        blk = self.blocks[s]
+        off = len(blk) * self.rank // self.world           # my share's place among the subset's projections
+        lib, npix = p.lib, f["npix"]
+        if count:
+            ev = None
+            if self.kernel_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            p.ax_residual(x_res, self.b[first:first + count], first, count, f["r"][off:off + count],
+                          self.w_variant, ss)
+            if ev is not None:
+                ev[1].record()
+                self.kernel_events.append((ev[0], ev[1], count))
+            self.launches += p.ax_launches(1)
+            # my residual projections into every rank's copy of the subset's set
+            self._timed("gather", lambda: _lib.check(lib.pax_bcast_chunks(
+                _vp(f["r"]), _vp_int(f["mc_r"]), f["r_peers"], self.world, npix * 4, off, 1, count, _cur_stream()),
+                "pax_bcast_chunks"))
+            self.launches += 1
+        self._timed("barrier", lambda: f["hr"].barrier(channel=0))          # every rank's residuals have landed
+        # all of the subset's angles into MY rows of the volume, SART update in the epilogue (as on one GPU) ...
+        self._timed("atb", lambda: self.plan_full.atb(f["r"], gfirst, glen, x_res, _lib.PAX_ATB_SART, self.inv_v[s],
+                                                      lam, noneg, rows=(self.rank, self.world)))
+        # ... and those rows to every rank
+        ny = p.ny
+        nrows = (ny - self.rank + self.world - 1) // self.world
+        self._timed("update", lambda: _lib.check(lib.pax_bcast_chunks(
+            _vp(x_res), _vp_int(f["mc_x"]), f["x_peers"], self.world, self.plan_full.nxp_nzp_bytes, self.rank + 1,
+            self.world, nrows, _cur_stream()), "pax_bcast_chunks"))
+        self._timed("barrier", lambda: f["hx"].barrier(channel=0))          # every row has landed everywhere
+        self.launches += 2
 
     def iteration(self, x_res, lam, noneg=True, computel2=False):
         for s in range(len(self.blocks)):

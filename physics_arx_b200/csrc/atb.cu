@@ -31,6 +31,7 @@ struct AtbArgs {
     float rdU, rdV, cu, cv;    // 1/dU, 1/dV, nU/2-0.5, nV/2-0.5
     float lambda;
     int mode, noneg;
+    int row_part, row_parts;   // only the rows y = row_part (mod row_parts)
 };
 
 __device__ __forceinline__ void atb_load_angles(AtbAngle *sm, const AngleDev *angles, int first,
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(128) k_atb(const AtbArgs a)
     __shared__ AtbAngle sm[ATB_MAX_ANGLES];
     atb_load_angles(sm, a.angles, a.first, a.count);
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int iy = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int iy = (blockIdx.y * 4 + (threadIdx.x >> 5)) * a.row_parts + a.row_part;
     const int kz = blockIdx.z * ATB_ZT;
     if (ix >= a.nx || iy >= a.ny) return;
 
@@ -152,7 +153,12 @@ extern "C" int pax_atb(const PaxPlan *p, const float *proj, int first, int count
     a.rdU = (float)(1.0 / g.dDetecU); a.rdV = (float)(1.0 / g.dDetecV);
     a.cu = (float)(0.5 * g.nDetecU - 0.5); a.cv = (float)(0.5 * g.nDetecV - 0.5);
     a.lambda = epi->lambda; a.noneg = epi->noneg;
-    dim3 grid(pax_cdiv(g.nVoxelX, 32), pax_cdiv(g.nVoxelY, 4), pax_cdiv(g.nVoxelZ, ATB_ZT));
+    a.row_parts = epi->row_parts > 1 ? epi->row_parts : 1;
+    a.row_part = a.row_parts > 1 ? epi->row_part : 0;
+    PAX_REQUIRE(a.row_part >= 0 && a.row_part < a.row_parts, "pax_atb: row share %d of %d", a.row_part, a.row_parts);
+    const int rows = (g.nVoxelY - a.row_part + a.row_parts - 1) / a.row_parts;
+    if (rows <= 0) return PAX_OK;
+    dim3 grid(pax_cdiv(g.nVoxelX, 32), pax_cdiv(rows, 4), pax_cdiv(g.nVoxelZ, ATB_ZT));
     cudaStream_t st = (cudaStream_t)stream;
     for (int off = 0; off < count; off += ATB_MAX_ANGLES) {
         a.first = first + off;

@@ -394,6 +394,53 @@ __global__ void __launch_bounds__(256) k_sart_update_fused(float *__restrict__ x
     // host side enqueues next on the same stream
 }
 
+// ---------------------------------------------------------------- broadcast of chunks of a symmetric buffer
+struct PeerDst {
+    char *p[PAX_MAX_PEERS];
+};
+
+template <bool MC>
+__global__ void __launch_bounds__(256) k_bcast_chunks(const char *__restrict__ src, char *dst_mc, const PeerDst peers,
+                                                      int world, size_t chunk16, long first, long stride)
+{
+    // blockIdx.y = chunk, grid-stride over its 16-byte units: a warp moves 512 contiguous bytes per instruction
+    const size_t off = ((size_t)first + (size_t)blockIdx.y * (size_t)stride) * chunk16 * 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunk16; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4 *>(src + off + i * 16);
+        if (MC) {
+            mc_st4(reinterpret_cast<float *>(dst_mc + off + i * 16), v);
+        } else {
+            for (int r = 0; r < world; ++r) *reinterpret_cast<float4 *>(peers.p[r] + off + i * 16) = v;
+        }
+    }
+}
+
+extern "C" int pax_bcast_chunks(const void *src_local, void *dst_mc, const uint64_t *dst_peers, int world,
+                                size_t chunk_bytes, long first_chunk, long chunk_stride, long n_chunks, void *stream)
+{
+    PAX_REQUIRE(src_local && (dst_mc || dst_peers), "pax_bcast_chunks: NULL argument");
+    PAX_REQUIRE(world >= 1 && world <= PAX_MAX_PEERS, "pax_bcast_chunks: world %d", world);
+    PAX_REQUIRE(chunk_bytes % 16 == 0 && ((uintptr_t)src_local & 15) == 0, "pax_bcast_chunks: 16-byte units");
+    PAX_REQUIRE(first_chunk >= 0 && chunk_stride >= 1 && n_chunks >= 0 && n_chunks < 65536, "pax_bcast_chunks: range");
+    if (n_chunks == 0 || chunk_bytes == 0) return PAX_OK;
+    PeerDst peers;
+    for (int r = 0; r < PAX_MAX_PEERS; ++r)
+        peers.p[r] = (!dst_mc && r < world) ? reinterpret_cast<char *>(dst_peers[r]) : nullptr;
+    const size_t c16 = chunk_bytes / 16;
+    const int bx = (int)((c16 + 255) / 256 < 64 ? (c16 + 255) / 256 : 64);
+    dim3 grid(bx, (unsigned)n_chunks);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_mc)
+        k_bcast_chunks<true><<<grid, 256, 0, st>>>(reinterpret_cast<const char *>(src_local),
+                                                   reinterpret_cast<char *>(dst_mc), peers, world, c16, first_chunk,
+                                                   chunk_stride);
+    else
+        k_bcast_chunks<false><<<grid, 256, 0, st>>>(reinterpret_cast<const char *>(src_local), nullptr, peers, world,
+                                                    c16, first_chunk, chunk_stride);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
 extern "C" int pax_sart_update_fused(const PaxPlan *p, float *x_local, float *x_mc, const float *upd_mc,
                                      const uint64_t *x_peers, const uint64_t *upd_peers, int rank, int world,
                                      const float *inv_v, float lambda, int noneg, void *stream)

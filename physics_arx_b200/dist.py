@@ -15,18 +15,19 @@ from __future__ import annotations
 import numpy as np
 
 
-def shard_blocks(blocks, rank, world):
+def shard_blocks(blocks, rank, world, contiguous=False):
     """Rank-local angle list and per-subset (first, count) ranges into it.
 
-    Rank r owns ``block[r::world]`` of every subset, concatenated in subset order, so the
-    union over ranks is every angle exactly once and the per-rank load differs by at most
-    one angle per subset.
+    Rank r owns ``block[r::world]`` of every subset (or, with ``contiguous``, the r-th of `world` consecutive
+    stretches of the block), concatenated in subset order, so the union over ranks is every angle exactly once
+    and the per-rank load differs by at most one angle per subset.
     """
     if not (0 <= rank < world):
         raise ValueError(f"rank {rank} outside world of {world}")
     local, ranges, pos = [], [], 0
     for blk in blocks:
-        mine = np.asarray(blk)[rank::world]
+        blk = np.asarray(blk)
+        mine = blk[len(blk) * rank // world:len(blk) * (rank + 1) // world] if contiguous else blk[rank::world]
         ranges.append((pos, len(mine)))
         local.append(mine)
         pos += len(mine)

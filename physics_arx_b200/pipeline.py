@@ -108,17 +108,8 @@ class SCBCTPipeline:
         st = self.st
         p = self.plan
         if self.v_variant == "A":      # set_v runs inside every ossart() call of the reference
-            import torch.distributed as dist
-            V = torch.zeros_like(st.inv_v)
-            for s, (first, count) in enumerate(st.ranges):
-                if count:
-                    p.compute_v(first, count, out=V[s])
-                    self.launches += 1
-            if st.tiles is not None:
-                V /= st.tiles[1]
-            if st.world > 1:
-                dist.all_reduce(V, group=st.group)
-            st.inv_v = torch.where(V > 1e-12, 1.0 / V, torch.zeros_like(V)).contiguous()
+            st.inv_v = st.compute_inv_v()
+            self.launches += len(st.blocks)
         self.x_res.zero_()
         lam = self.lmbda
         n0 = st.launches

@@ -78,6 +78,9 @@ class Plan:
                                                 self.n_angles, ctypes.byref(handle)), "pax_plan_create")
         self._h = handle
         self.vol_elems = int(self.lib.pax_vol_elems(self._h))
+        self.nzp = ((self.nz + 5) + 3) // 4 * 4          # resident layout (include/pax.h): (Y+2, X+2, Zp), z fastest
+        self.nxp_nzp_bytes = (self.nx + 2) * self.nzp * 4  # one y-row of it
+        assert (self.ny + 2) * (self.nx + 2) * self.nzp == self.vol_elems
         self._work = None              # Ax scratch (quad-packed volume), grown on demand
         # PAX_AX_KERNEL / projector=: auto (default) | fan | ray (= quad) | plain  (include/pax.h)
         kind = (projector or os.environ.get("PAX_AX_KERNEL", "auto")).lower()
@@ -216,9 +219,12 @@ class Plan:
                                        ctypes.byref(epi), _ptr(self._workspace(1)), _stream()), "pax_ax")
         return out
 
-    def atb(self, proj, first, count, out_res, mode=_lib.PAX_ATB_STORE, inv_v=None, lam=1.0, noneg=True):
+    def atb(self, proj, first, count, out_res, mode=_lib.PAX_ATB_STORE, inv_v=None, lam=1.0, noneg=True,
+            rows=None):
+        """rows=(part, parts): only the volume rows y = part (mod parts) (multi-GPU row shares)."""
         epi = _lib.PaxAtbEpilogue(mode, int(bool(noneg)), float(lam),
-                                  inv_v.data_ptr() if inv_v is not None else None)
+                                  inv_v.data_ptr() if inv_v is not None else None,
+                                  int(rows[0]) if rows else 0, int(rows[1]) if rows else 0)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_atb(self._h, _ptr(proj), first, count, _ptr(out_res),
                                         ctypes.byref(epi), _stream()), "pax_atb")

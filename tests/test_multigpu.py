@@ -46,9 +46,9 @@ def _worker(rank, world, port, q, shard):
     elif shard == "tiles":
         del os.environ["PAX_FUSED_UPDATE"]
         shard, want = (1, world), "fused"
-    elif shard == "default":                # what a caller gets: the fused kernel, auto grid
-        del os.environ["PAX_FUSED_UPDATE"]
-        shard, want = "auto", "fused"
+    elif shard == "default":                # what a caller gets: the gather scheme (residual all-gather, row-owned
+        del os.environ["PAX_FUSED_UPDATE"]  # backprojection + update, row broadcast)
+        shard, want = "auto", "gather"
     if shard == "grid":                     # 2 angle groups x (world/2) bands of detector columns
         shard = (2, world // 2)
     pipe = SCBCTPipeline(geo, angles, group=dist.group.WORLD, shard=shard, **kw)
@@ -58,7 +58,10 @@ def _worker(rank, world, port, q, shard):
         assert pipe.st.shard == (shard if isinstance(shard, str) else ("grid" if world > 2 else "angles"))
     sharded = pipe.run_host(ct, art).numpy().copy()
     coll = "nccl" if pipe.st.fused is None else pipe.st.fused["kind"]
-    if want == "fused":
+    if want == "gather":
+        assert pipe.st.scheme == "gather", getattr(pipe.st, "gather_error", "")
+        coll = "gather, " + pipe.st.gsym["kind"]
+    elif want == "fused":
         assert pipe.st.fused is not None, getattr(pipe.st, "fused_error", "")
     else:
         assert coll == want, (coll, getattr(pipe.st, "fused_error", ""))
