@@ -178,6 +178,12 @@ int pax_sart_update(const PaxPlan *plan, float *x_res, const float *upd_res, con
 int pax_bcast_chunks(const void *src_local, void *dst_mc, const uint64_t *dst_peers, int world, size_t chunk_bytes,
                      long first_chunk, long chunk_stride, long n_chunks, void *stream);
 
+/* The same for the iterate: the rows y = part (mod parts) of this rank's resident volume to every rank, skipping
+ * the columns with inv_v == 0 (not seen by the subset, hence not updated).  After pax_atb(..., PAX_ATB_SART,
+ * row_part/row_parts) has updated exactly those rows. */
+int pax_bcast_xrows(const PaxPlan *plan, const float *x_local, float *x_mc, const uint64_t *x_peers, int world,
+                    const float *inv_v, int part, int parts, void *stream);
+
 int pax_sart_update_fused(const PaxPlan *plan, float *x_local, float *x_mc, const float *upd_mc,
                           const uint64_t *x_peers, const uint64_t *upd_peers, int rank, int world,
                           const float *inv_v, float lambda, int noneg, void *stream);

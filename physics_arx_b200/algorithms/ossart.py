@@ -401,11 +401,9 @@ class OSSARTState:
         self._timed("atb", lambda: self.plan_full.atb(f["r"], gfirst, glen, x_res, _lib.PAX_ATB_SART, self.inv_v[s],
                                                       lam, noneg, rows=(self.rank, self.world)))
         # ... and those rows to every rank
-        ny = p.ny
-        nrows = (ny - self.rank + self.world - 1) // self.world
-        self._timed("update", lambda: _lib.check(lib.pax_bcast_chunks(
-            _vp(x_res), _vp_int(f["mc_x"]), f["x_peers"], self.world, self.plan_full.nxp_nzp_bytes, self.rank + 1,
-            self.world, nrows, _cur_stream()), "pax_bcast_chunks"))
+        self._timed("update", lambda: _lib.check(lib.pax_bcast_xrows(
+            self.plan_full._h, _vp(x_res), _vp_int(f["mc_x"]), f["x_peers"], self.world, _vp(self.inv_v[s]),
+            self.rank, self.world, _cur_stream()), "pax_bcast_xrows"))
         self._timed("barrier", lambda: f["hx"].barrier(channel=0))          # every row has landed everywhere
         self.launches += 2
 

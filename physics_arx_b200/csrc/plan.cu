@@ -441,6 +441,51 @@ extern "C" int pax_bcast_chunks(const void *src_local, void *dst_mc, const uint6
     return PAX_OK;
 }
 
+// The volume rows a rank owns (y = part mod parts), to every rank -- but only the columns the subset's rays see
+// (inv_v != 0): the others were not updated, so every rank holds them already.  About half of the plane at C2.
+template <bool MC>
+__global__ void __launch_bounds__(256) k_bcast_xrows(const float *__restrict__ x_local, float *x_mc, const PeerDst peers,
+                                                     int world, const float *__restrict__ inv_v, int nz, int nx,
+                                                     int nxp, int nzp, int part, int parts, long n_local)
+{
+    const int nz4 = (nz + 3) / 4;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_local) return;
+    const int q = (int)(t % nz4);
+    const long cl = t / nz4;
+    const int yy = (int)(cl / nx) * parts + part, xx = (int)(cl % nx);
+    if (inv_v[(long)yy * nx + xx] == 0.f) return;
+    const size_t base = ((size_t)(yy + 1) * nxp + (xx + 1)) * nzp + PAX_ZOFF + 4 * q;
+    const float4 v = *reinterpret_cast<const float4 *>(x_local + base);      // (the rim beyond nz holds zeros)
+    if (MC) mc_st4(x_mc + base, v);
+    else
+        for (int r = 0; r < world; ++r) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(peers.p[r]) + base) = v;
+}
+
+extern "C" int pax_bcast_xrows(const PaxPlan *p, const float *x_local, float *x_mc, const uint64_t *x_peers, int world,
+                               const float *inv_v, int part, int parts, void *stream)
+{
+    PAX_REQUIRE(p && x_local && inv_v && (x_mc || x_peers), "pax_bcast_xrows: NULL argument");
+    PAX_REQUIRE(world >= 1 && world <= PAX_MAX_PEERS && parts >= 1 && part >= 0 && part < parts,
+                "pax_bcast_xrows: share %d of %d, world %d", part, parts, world);
+    const long rows = (p->geo.nVoxelY - part + parts - 1) / parts;
+    const long n_local = rows * p->geo.nVoxelX * ((p->geo.nVoxelZ + 3) / 4);
+    if (n_local <= 0) return PAX_OK;
+    PeerDst peers;
+    for (int r = 0; r < PAX_MAX_PEERS; ++r)
+        peers.p[r] = (!x_mc && r < world) ? reinterpret_cast<char *>(x_peers[r]) : nullptr;
+    const int blocks = pax_cdiv(n_local, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_mc)
+        k_bcast_xrows<true><<<blocks, 256, 0, st>>>(x_local, x_mc, peers, world, inv_v, p->geo.nVoxelZ, p->geo.nVoxelX,
+                                                    p->nxp, p->nzp, part, parts, n_local);
+    else
+        k_bcast_xrows<false><<<blocks, 256, 0, st>>>(x_local, nullptr, peers, world, inv_v, p->geo.nVoxelZ,
+                                                     p->geo.nVoxelX, p->nxp, p->nzp, part, parts, n_local);
+    PAX_CHECK_CUDA(cudaGetLastError());
+    return PAX_OK;
+}
+
 extern "C" int pax_sart_update_fused(const PaxPlan *p, float *x_local, float *x_mc, const float *upd_mc,
                                      const uint64_t *x_peers, const uint64_t *upd_peers, int rank, int world,
                                      const float *inv_v, float lambda, int noneg, void *stream)
