@@ -145,11 +145,16 @@ int pax_vol_axpy(const PaxPlan *plan, float *y_res, const float *x_res, float a,
 
 /* tigre.Ax(img, geo, angles, 'interpolated')  -- reference :86; angles [first, first+count)
  * of the plan; vol_res1 may be NULL (single channel). proj_out is (count,V,U).
- * workspace (RAY kernel only; pax_ax_workspace_bytes is 0 when the plan resolves to FAN): device
+ * workspace, RAY kernel (pax_ax_workspace_bytes is 0 when the plan resolves to FAN): device
  * scratch of pax_ax_workspace_bytes(plan, channels) bytes, 16-byte aligned, that receives the
  * gather-friendly re-packing of the volume(s) for this call; NULL selects the slower ray kernel
- * that gathers from the resident layout directly. */
+ * that gathers from the resident layout directly.
+ * workspace, FAN kernel: optional device scratch of pax_ax_fan_scratch_bytes(plan, count) bytes (0: none
+ * wanted).  A launch too small to fill the GPU a few times over -- a rank's few angles in a multi-GPU
+ * run -- is then cut into up to four parts along the chords, whose raw sums go to the scratch and are
+ * added up by a second, elementwise kernel; NULL keeps the single launch. */
 size_t pax_ax_workspace_bytes(const PaxPlan *plan, int n_channels);
+size_t pax_ax_fan_scratch_bytes(const PaxPlan *plan, int count);
 int pax_ax(const PaxPlan *plan, const float *vol_res0, const float *vol_res1, int first, int count,
            float *proj_out, const PaxAxEpilogue *epi, void *workspace, void *stream);
 

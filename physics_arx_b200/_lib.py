@@ -61,6 +61,7 @@ SYMBOLS = [
     ("pax_max_decode", ctypes.c_int, [_VP, _VP]),
     ("pax_lincomb", ctypes.c_int, [_VP, _VP, _VP, ctypes.c_float, ctypes.c_float, ctypes.c_size_t, _VP]),
     ("pax_ax_workspace_bytes", ctypes.c_size_t, [_VP, ctypes.c_int]),
+    ("pax_ax_fan_scratch_bytes", ctypes.c_size_t, [_VP, ctypes.c_int]),
     ("pax_ax", ctypes.c_int, [_VP, _VP, _VP, ctypes.c_int, ctypes.c_int, _VP,
                               ctypes.POINTER(PaxAxEpilogue), _VP, _VP]),
     ("pax_atb", ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP,

@@ -40,6 +40,9 @@ def _cur_stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_NVTX = __import__("os").environ.get("PAX_NVTX", "") == "1"
+
+
 def os_environ(name):
     import os
     return os.environ.get(name, "")
@@ -310,6 +313,12 @@ class OSSARTState:
     def _timed(self, name, fn):
         """Run fn(); with kernel_events enabled also bracket it with CUDA events under `name` (bench breakdown)."""
         if self.kernel_events is None:
+            if _NVTX:                  # PAX_NVTX=1: named ranges around the phases of a subset step (nsys / ncu)
+                torch.cuda.nvtx.range_push("pax:" + name)
+                try:
+                    return fn()
+                finally:
+                    torch.cuda.nvtx.range_pop()
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

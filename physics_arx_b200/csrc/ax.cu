@@ -354,7 +354,8 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
     a.a0 = epi->a0; a.a1 = epi->a1; a.c = epi->c;
     a.accumulate = 0;
     a.whx = epi->w_half_x; a.why = epi->w_half_y; a.whz = epi->w_half_z; a.wthr = epi->w_thr;
-    a.fan_rows = 0; a.fan_epoch = 0; a.fan_count = 0; a.fan_order = nullptr; a.fan_ntiles = 0;
+    a.fan_rows = 0; a.fan_epoch = 0; a.fan_count = 0; a.fan_order = nullptr; a.fan_ntiles = 0; a.fan_split = 1;
+    a.fan_scratch = reinterpret_cast<float *>(workspace);      // (fan projector: optional scratch of a split launch)
     cudaStream_t st = (cudaStream_t)stream;
     PAX_REQUIRE(p->fan_share_parts == 1 || pax_plan_projector(p) == PAX_PROJECTOR_FAN,
                 "pax_ax: a column share (pax_plan_set_column_share) needs the fan-plane projector");

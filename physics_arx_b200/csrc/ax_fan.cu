@@ -195,8 +195,12 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
 
     if (hit && lam0 <= lam1) {
         const int Emin = max((int)floor(lam0 * (double)nlo), 0), Emax = (int)ceil(lam1 * (double)nhi);
+        // a launch too small to fill the GPU more than a few times over is cut into `fan_split` parts along the
+        // chord (whole epochs: their sums are independent), one warp each; k_fan_finish adds the parts up
+        const int nep = (Emax - Emin) / EP + 1;
+        const int mA = nep * (int)blockIdx.z / a.fan_split, mB = nep * ((int)blockIdx.z + 1) / a.fan_split;
 #pragma unroll 1
-        for (int e0 = Emin; e0 <= Emax; e0 += EP) {
+        for (int e0 = Emin + mA * EP; e0 < Emin + mB * EP; e0 += EP) {
             const int e1 = min(e0 + EP - 1, Emax);
             const int ref = e0 + (EP >> 1);
             const int nwin = (e1 - e0 + CW) / CW;
@@ -489,6 +493,11 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     }
     __syncwarp();
 
+    if (a.fan_split > 1) {                                        // raw sums of my part; k_fan_finish does the rest
+        float *dst = a.fan_scratch + (((size_t)blockIdx.z * a.fan_count + ia) * a.nv + V0) * a.nu + u;
+        for (int r = lane; r < nRows; r += 32) dst[(size_t)r * a.nu] = rsum[r];
+        return;
+    }
     // ---- epilogue, run by run (the step length in mm depends on n).  The warps of the CTA own adjacent columns and
     // fill one 32-byte sector of every row between them; L2 merges the partial writes.
     int cur = 0;
@@ -551,7 +560,73 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     }
 }
 
+// The epilogue of a split launch: add the parts of every pixel up, scale by the step length of the pixel's ray
+// (same arithmetic as above) and apply the PLAIN / RESIDUAL epilogue.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fan_finish(const AxArgs a)
+{
+    const size_t npix = (size_t)a.nv * a.nu, n = npix * a.fan_count;
+    const double racc = 1.0 / a.acc;
+    float r2 = 0.f, mymax = -INFINITY;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int ia = (int)(e / npix), v = (int)((e % npix) / a.nu), u = (int)(e % a.nu);
+        float sum = 0.f;
+        for (int k = 0; k < a.fan_split; ++k) sum += a.fan_scratch[(size_t)k * n + e];
+        const AngleDev &A = a.angles[a.first + ia];
+        const double dx = A.ox + u * A.ux - A.sx, dy = A.oy + u * A.uy - A.sy, dz = A.oz + (double)v * A.vz - A.sz;
+        const int nrun = (int)ceil(sqrt(dx * dx + dy * dy + dz * dz) * racc);
+        const double rn = 1.0 / (double)nrun;
+        const double mx = dx * rn * a.dX, my = dy * rn * a.dY, mz = dz * rn * a.dZ;
+        const float p0 = sum * (float)sqrt(mx * mx + my * my + mz * mz);
+        if (MODE == PAX_AX_PLAIN) {
+            float val = a.a0 * p0;
+            if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
+            if (a.accumulate) val += a.out[e];
+            a.out[e] = val;
+            mymax = fmaxf(mymax, val);
+        } else {
+            const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
+            const float w = L > a.wthr ? 1.f / L : 0.f;
+            const float r_ = __ldg(a.b + e) - p0;
+            r2 = fmaf(r_, r_, r2);
+            a.out[e] = w * r_;
+        }
+    }
+    if (MODE == PAX_AX_PLAIN && a.maxout) {
+        for (int o = 16; o; o >>= 1) mymax = fmaxf(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
+        if ((threadIdx.x & 31) == 0 && mymax > -INFINITY) {
+            const unsigned b = __float_as_uint(mymax);
+            atomicMax(a.maxout, (b & 0x80000000u) ? ~b : (b | 0x80000000u));
+        }
+    }
+    if (MODE == PAX_AX_RESIDUAL && a.sumsq) {
+        for (int o = 16; o; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.sumsq, (double)r2);
+    }
+}
+
 // ------------------------------------------------------------------------------ host side
+// Parts a launch of `count` angles is cut into along the chords: none while its warps fill the GPU's 16 warp slots
+// per SM three times over, else as many as that takes (at most 4; a chord has 6-9 epochs at C2).
+static int fan_parts(const PaxPlan *p, int count)
+{
+    const char *e = getenv("PAX_FAN_SPLIT");                    // tuning hook / tests: force 1..4 parts
+    if (e && atoi(e) >= 1 && atoi(e) <= 4) return atoi(e);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    const long warps = (long)p->fan_ntiles * p->fan_warps * count * pax_cdiv(p->geo.nDetecV, p->fan_rows);
+    const long want = 3L * sms * 16;
+    if (warps <= 0 || warps >= want) return 1;
+    return (int)std::min(4L, (want + warps - 1) / warps);
+}
+
+extern "C" size_t pax_ax_fan_scratch_bytes(const PaxPlan *p, int count)
+{
+    if (!p || count < 1 || pax_plan_projector(p) != PAX_PROJECTOR_FAN || p->fan_epoch < 1) return 0;
+    const int parts = fan_parts(p, count);
+    return parts > 1 ? (size_t)parts * count * p->geo.nDetecV * p->geo.nDetecU * sizeof(float) : 0;
+}
+
 template <int CW, int NWARPS, int MINB, int MODE>
 static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
 {
@@ -562,9 +637,14 @@ static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AxArgs b = a;
     b.fan_count = count;
-    dim3 grid(a.fan_ntiles * count, pax_cdiv(a.nv, a.fan_rows));
+    dim3 grid(a.fan_ntiles * count, pax_cdiv(a.nv, a.fan_rows), a.fan_split);
     if (a.fan_ntiles == 0) return PAX_OK;
     k_ax_fan<CW, NWARPS, MINB, MODE><<<grid, NWARPS * 32, smem, st>>>(b);
+    if (a.fan_split > 1) {
+        const size_t n = (size_t)count * a.nv * a.nu;
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+        k_fan_finish<MODE><<<blocks, 256, 0, st>>>(b);
+    }
     return PAX_OK;
 }
 
@@ -583,6 +663,10 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     a.fault = p->d_fault;
     a.fan_order = p->d_fan_order;
     a.fan_ntiles = p->fan_ntiles;
+    // split along the chords when the launch is small and the caller gave the scratch for it (a0.fan_scratch);
+    // not with a column share (its columns are not the whole detector), nor when samples are counted
+    a.fan_split = (a0.fan_scratch && !a0.nsamples && p->fan_share_parts == 1) ? fan_parts(p, count) : 1;
+    if (a.fan_split == 1) a.fan_scratch = nullptr;
     PAX_REQUIRE(a.fan_order, "pax_ax: the fan-plane projector was not configured for this plan");
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
     PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");

@@ -81,6 +81,8 @@ struct AxArgs {
     int fan_count;                // ax_fan.cu: angles of the launch
     const int *fan_order;         // ax_fan.cu: column tiles in launch order (longest chords first)
     int fan_ntiles;               // ax_fan.cu: how many of them
+    int fan_split;                // ax_fan.cu: parts the launch is cut into along the chords (1: none)
+    float *fan_scratch;           // ax_fan.cu: [fan_split][count][V][U] raw sums of a split launch
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
     int *fault;                   // ax_fan.cu: set to 1 if a single row's z range did not fit the lanes (never, by construction)
 };

@@ -134,7 +134,7 @@ class Plan:
     def ax_launches(self, channels=1):
         """kernels one pax_ax call launches (bench.py's gpu_launches claim)."""
         if self.projector == "fan":
-            return channels
+            return channels            # (+ 1 finish kernel per channel when a small launch is split)
         return 1 + (channels if self._workspace(channels) is not None else 0)
 
     # ------------------------------------------------------------------ volumes
@@ -163,11 +163,15 @@ class Plan:
             _lib.check(self.lib.pax_vol_unpack(self._h, _ptr(res), _ptr(out), _stream()), "pax_vol_unpack")
         return out
 
-    def _workspace(self, channels):
+    def _workspace(self, channels, count=None):
+        """Scratch pax_ax wants for this call: the ray kernel's re-packed volume(s), or -- fan kernel, small
+        launches only -- the partial sums of a launch split along the chords (include/pax.h)."""
         if not self.use_workspace:
             return None
         need = int(self.lib.pax_ax_workspace_bytes(self._h, channels))
-        if need == 0:                  # geometry outside the workspace kernel's range
+        if need == 0 and count is not None:
+            need = int(self.lib.pax_ax_fan_scratch_bytes(self._h, int(count)))
+        if need == 0:                  # geometry outside the workspace kernel's range / nothing wanted
             return None
         if self._work is None or self._work.numel() * 4 < need:
             self._work = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
@@ -203,7 +207,7 @@ class Plan:
             maxout.zero_()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_ax(self._h, _ptr(res0), _ptr(res1), first, count, _ptr(out),
-                                       ctypes.byref(epi), _ptr(self._workspace(1 if res1 is None else 2)),
+                                       ctypes.byref(epi), _ptr(self._workspace(1 if res1 is None else 2, count)),
                                        _stream()), "pax_ax")
             if maxout is not None:    # maxout: 1-element float32 tensor, holds max(out) afterwards
                 _lib.check(self.lib.pax_max_decode(_ptr(maxout), _stream()), "pax_max_decode")
@@ -216,7 +220,7 @@ class Plan:
                                  sumsq.data_ptr() if sumsq is not None else None, None, None, None)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pax_ax(self._h, _ptr(res), None, first, count, _ptr(out),
-                                       ctypes.byref(epi), _ptr(self._workspace(1)), _stream()), "pax_ax")
+                                       ctypes.byref(epi), _ptr(self._workspace(1, count)), _stream()), "pax_ax")
         return out
 
     def atb(self, proj, first, count, out_res, mode=_lib.PAX_ATB_STORE, inv_v=None, lam=1.0, noneg=True,

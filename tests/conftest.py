@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: a minute or more (the float64 oracle at a full benchmark size)")
 
 
 def pytest_collection_modifyitems(config, items):

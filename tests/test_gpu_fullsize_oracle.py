@@ -162,3 +162,26 @@ def test_fan_projector_matches_oracle_on_random_geometries(oracle):
 
     run()
     assert len(seen) >= 10
+
+
+@pytest.mark.slow
+def test_c1_full_size_pipeline_matches_oracle(oracle):
+    """BASELINE.json's configuration C1 at FULL size (128^3 @ 2 mm, 256 angles, 256x256 detector @ 2 mm,
+    scatter + noise induction, 5-iteration OS-SART with blocksize 20) -- "the reference's CPU-runnable case" --
+    through the same sequence on the float64 oracle: about a minute of CPU."""
+    from physics_arx_b200.phantom import artifact_volume, config_c1, lung_phantom
+    from physics_arx_b200.pipeline import SCBCTPipeline
+    cfg = config_c1()
+    geo, angles = cfg["geo"], cfg["angles"]
+    ct = lung_phantom(geo.nVoxel, geo.dVoxel, seed=0)
+    art = artifact_volume(geo.nVoxel, seed=1)
+    pipe = SCBCTPipeline(geo, angles, niter=cfg["niter"], blocksize=cfg["blocksize"], I0=cfg["I0"], sigma=cfg["sigma"],
+                         scatter_scale=0.5, seed=5)
+    got = pipe.run_host(ct, art).numpy()
+    p = oracle.ax(ct.astype(np.float64) + 0.5 * art.astype(np.float64), geo, angles)
+    p = oracle.ctnoise_add(p.astype(np.float32), Poisson=cfg["I0"], Gaussian=np.array([0.0, cfg["sigma"]]), seed=5)
+    ref = oracle.ossart(p.astype(np.float32), geo, angles, cfg["niter"], blocksize=cfg["blocksize"])
+    d = np.abs(got.astype(np.float64) - ref) * HU
+    print("C1 full size: mean |dHU|", d.mean(), "max", d.max())
+    assert d.mean() <= 1.0 and d.max() <= 5.0, (d.mean(), d.max())
+    assert d.mean() <= 0.01, d.mean()

@@ -362,3 +362,33 @@ def test_c1_like_pipeline_matches_oracle_after_five_iterations(oracle):
     d = np.abs(got.astype(np.float64) - ref) * HU
     assert d.mean() <= 1.0 and d.max() <= 5.0, (d.mean(), d.max())
     assert d.mean() <= 0.01, d.mean()          # in practice three orders of magnitude inside the tolerance
+
+
+@pytest.mark.parametrize("parts", [2, 3, 4])
+def test_fan_projector_split_along_the_chords(oracle, parts, monkeypatch):
+    """A small launch (a rank's few angles in a multi-GPU run) is cut into parts along the chords and summed by
+    a finish kernel (include/pax.h: pax_ax_fan_scratch_bytes).  Forced here: same projections, same residual."""
+    torch = _torch()
+    from physics_arx_b200.projector import Plan
+    name, geo, angles = _fan_cases()[2]
+    rng = np.random.default_rng(13)
+    vol = rng.random(tuple(int(v) for v in geo.nVoxel)).astype(np.float32)
+    plan = Plan(geo, angles, projector="fan")
+    res = plan.pack(torch.from_numpy(vol).cuda())
+    whole = plan.ax(res).cpu().numpy()
+    monkeypatch.setenv("PAX_FAN_SPLIT", str(parts))
+    m = torch.zeros(1, device="cuda")
+    split = plan.ax(res, maxout=m)
+    assert plan._work is not None and plan.fault() == 0
+    assert rel_l2(split.cpu().numpy(), whole) <= 5e-7
+    assert rel_l2(split.cpu().numpy(), oracle.ax(vol, geo, angles)) <= 2e-6
+    assert float(m.item()) == float(split.max().item())
+    b = (split * 1.1).contiguous()
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    out = torch.empty_like(split)
+    plan.ax_residual(res, b, 0, len(angles), out, sumsq=ss)
+    monkeypatch.delenv("PAX_FAN_SPLIT")
+    want = torch.empty_like(split)
+    plan.ax_residual(res, b, 0, len(angles), want)
+    assert rel_l2(out.cpu().numpy(), want.cpu().numpy()) <= 1e-5
+    assert abs(float(ss.item()) - float(((b - split) ** 2).sum().item())) <= 1e-4 * float(ss.item())
