@@ -182,6 +182,11 @@ int pax_sart_update(const PaxPlan *plan, float *x_res, const float *upd_res, con
  * one row of the resident volume, stride = world).  The caller synchronises the ranks around it. */
 int pax_bcast_chunks(const void *src_local, void *dst_mc, const uint64_t *dst_peers, int world, size_t chunk_bytes,
                      long first_chunk, long chunk_stride, long n_chunks, void *stream);
+/* The general form: the chunks are read from `src` starting at chunk src_first_chunk (-1: from the same place
+ * as in the destination), and with add != 0 they are ADDED to what every rank's buffer holds (multimem.red --
+ * ranks that each computed some columns of a projection, zeros elsewhere, merge them into a zeroed slot). */
+int pax_bcast_chunks2(const void *src, long src_first_chunk, void *dst_mc, const uint64_t *dst_peers, int world,
+                      size_t chunk_bytes, long first_chunk, long chunk_stride, long n_chunks, int add, void *stream);
 
 /* The same for the iterate: the rows y = part (mod parts) of this rank's resident volume to every rank, skipping
  * the columns with inv_v == 0 (not seen by the subset, hence not updated).  After pax_atb(..., PAX_ATB_SART,

@@ -69,6 +69,8 @@ SYMBOLS = [
     ("pax_sart_update", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_float, ctypes.c_int, _VP]),
     ("pax_bcast_chunks", ctypes.c_int, [_VP, _VP, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_size_t,
                                         ctypes.c_long, ctypes.c_long, ctypes.c_long, _VP]),
+    ("pax_bcast_chunks2", ctypes.c_int, [_VP, ctypes.c_long, _VP, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int,
+                                         ctypes.c_size_t, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_int, _VP]),
     ("pax_bcast_xrows", ctypes.c_int, [_VP, _VP, _VP, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, _VP,
                                        ctypes.c_int, ctypes.c_int, _VP]),
     ("pax_sart_update_fused", ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_uint64),

@@ -95,8 +95,8 @@ class OSSARTState:
         # the ranks form an A x R grid: the angles of every subset over A groups, the detector over R bands
         # (of columns, or of rows with shard='rows')
         self.grid = choose_shard(self.blocks, self.world, shard) if self.world > 1 else (1, 1)
-        if self.scheme == "gather":
-            self.grid = (self.world, 1)
+        if self.scheme == "gather" and self.plan_full.projector != "fan":
+            self.grid = (self.world, 1)          # column-tile shares need the fan projector: angles only
         A, R = self.grid
         self.axis = band_axis(shard)
         self.shard = "angles" if R == 1 else (self.axis if A == 1 else "grid")
@@ -112,7 +112,14 @@ class OSSARTState:
         sub_geo = subset_geometry(geo, plan_idx, n)
         self.tiles = None              # (part, parts): this rank's share of the detector's column tiles
         plan = None
-        if R > 1 and self.axis == "cols":
+        if R > 1 and self.scheme == "gather":
+            # the R ranks of an angle group project the same angles on shares of the detector's column tiles; their
+            # residuals (zeros in the columns of the others) are ADDED into the subset's symmetric residual set
+            plan = Plan(sub_geo, angles[plan_idx], device=dev.index)
+            plan.set_column_share(rr, R)
+            self.tiles = (rr, R)
+            self.u0, self.u1 = 0, nu
+        elif R > 1 and self.axis == "cols":
             # Where the fan-plane projector runs, the bands are not contiguous: every rank keeps the WHOLE detector
             # and its kernel walks every R-th column tile, dealt out by decreasing chord length -- contiguous bands
             # of a half-fan detector differ by 1.5x in work.  The columns of the other ranks stay zero in the
@@ -387,23 +394,32 @@ class OSSARTState:
         first, count = self.ranges[s]
         gfirst, glen = f["granges"][s]
         blk = self.blocks[s]
-        off = len(blk) * self.rank // self.world           # my share's place among the subset's projections
+        A, R = self.grid
+        off = len(blk) * (self.rank % A) // A              # my angle group's place among the subset's projections
         lib, npix = p.lib, f["npix"]
         if count:
             ev = None
             if self.kernel_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            p.ax_residual(x_res, self.b[first:first + count], first, count, f["r"][off:off + count],
-                          self.w_variant, ss)
+            # alone in my angle group: straight into my slice of the symmetric set; with column shares: into a
+            # local buffer whose other columns stay zero
+            dst = f["r"][off:off + count] if R == 1 else self.resid[:count]
+            p.ax_residual(x_res, self.b[first:first + count], first, count, dst, self.w_variant, ss)
             if ev is not None:
                 ev[1].record()
                 self.kernel_events.append((ev[0], ev[1], count))
             self.launches += p.ax_launches(1)
-            # my residual projections into every rank's copy of the subset's set
-            self._timed("gather", lambda: _lib.check(lib.pax_bcast_chunks(
-                _vp(f["r"]), _vp_int(f["mc_r"]), f["r_peers"], self.world, npix * 4, off, 1, count, _cur_stream()),
-                "pax_bcast_chunks"))
+            # my residual projections into every rank's copy of the subset's set (added, when the ranks of a
+            # group each hold some of a projection's columns)
+            if R == 1:
+                self._timed("gather", lambda: _lib.check(lib.pax_bcast_chunks(
+                    _vp(f["r"]), _vp_int(f["mc_r"]), f["r_peers"], self.world, npix * 4, off, 1, count,
+                    _cur_stream()), "pax_bcast_chunks"))
+            else:
+                self._timed("gather", lambda: _lib.check(lib.pax_bcast_chunks2(
+                    _vp(self.resid), 0, _vp_int(f["mc_r"]), f["r_peers"], self.world, npix * 4, off, 1, count, 1,
+                    _cur_stream()), "pax_bcast_chunks2"))
             self.launches += 1
         self._timed("barrier", lambda: f["hr"].barrier(channel=0))          # every rank's residuals have landed
         # all of the subset's angles into MY rows of the volume, SART update in the epilogue (as on one GPU) ...
@@ -413,6 +429,8 @@ class OSSARTState:
         self._timed("update", lambda: _lib.check(lib.pax_bcast_xrows(
             self.plan_full._h, _vp(x_res), _vp_int(f["mc_x"]), f["x_peers"], self.world, _vp(self.inv_v[s]),
             self.rank, self.world, _cur_stream()), "pax_bcast_xrows"))
+        if R > 1:
+            f["r"][:glen].zero_()                          # the next subset's residuals are added into zeros
         self._timed("barrier", lambda: f["hx"].barrier(channel=0))          # every row has landed everywhere
         self.launches += 2
 

@@ -563,15 +563,22 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
 // The epilogue of a split launch: add the parts of every pixel up, scale by the step length of the pixel's ray
 // (same arithmetic as above) and apply the PLAIN / RESIDUAL epilogue.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_fan_finish(const AxArgs a)
+__global__ void __launch_bounds__(256) k_fan_finish(const AxArgs a, int nwarps)
 {
-    const size_t npix = (size_t)a.nv * a.nu, n = npix * a.fan_count;
+    // one thread per pixel of the launch's column tiles (all of the detector, or this plan's share of it)
+    const size_t npix = (size_t)a.nv * a.nu, nall = npix * a.fan_count;
+    const size_t per_angle = (size_t)a.fan_ntiles * nwarps * a.nv, n = per_angle * a.fan_count;
     const double racc = 1.0 / a.acc;
     float r2 = 0.f, mymax = -INFINITY;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        const int ia = (int)(e / npix), v = (int)((e % npix) / a.nu), u = (int)(e % a.nu);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int ia = (int)(t / per_angle);
+        const size_t w = t % per_angle;
+        const int j = (int)(w % nwarps), v = (int)((w / nwarps) % a.nv), ti = (int)(w / ((size_t)nwarps * a.nv));
+        const int u = a.fan_order[ti] * nwarps + j;
+        if (u >= a.nu) continue;
+        const size_t e = ((size_t)ia * a.nv + v) * a.nu + u;
         float sum = 0.f;
-        for (int k = 0; k < a.fan_split; ++k) sum += a.fan_scratch[(size_t)k * n + e];
+        for (int k = 0; k < a.fan_split; ++k) sum += a.fan_scratch[(size_t)k * nall + e];
         const AngleDev &A = a.angles[a.first + ia];
         const double dx = A.ox + u * A.ux - A.sx, dy = A.oy + u * A.uy - A.sy, dz = A.oz + (double)v * A.vz - A.sz;
         const int nrun = (int)ceil(sqrt(dx * dx + dy * dy + dz * dz) * racc);
@@ -586,10 +593,10 @@ __global__ void __launch_bounds__(256) k_fan_finish(const AxArgs a)
             mymax = fmaxf(mymax, val);
         } else {
             const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
-            const float w = L > a.wthr ? 1.f / L : 0.f;
+            const float wt = L > a.wthr ? 1.f / L : 0.f;
             const float r_ = __ldg(a.b + e) - p0;
             r2 = fmaf(r_, r_, r2);
-            a.out[e] = w * r_;
+            a.out[e] = wt * r_;
         }
     }
     if (MODE == PAX_AX_PLAIN && a.maxout) {
@@ -641,9 +648,9 @@ static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
     if (a.fan_ntiles == 0) return PAX_OK;
     k_ax_fan<CW, NWARPS, MINB, MODE><<<grid, NWARPS * 32, smem, st>>>(b);
     if (a.fan_split > 1) {
-        const size_t n = (size_t)count * a.nv * a.nu;
+        const size_t n = (size_t)count * a.nv * a.fan_ntiles * NWARPS;
         const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-        k_fan_finish<MODE><<<blocks, 256, 0, st>>>(b);
+        k_fan_finish<MODE><<<blocks, 256, 0, st>>>(b, NWARPS);
     }
     return PAX_OK;
 }
@@ -664,8 +671,8 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     a.fan_order = p->d_fan_order;
     a.fan_ntiles = p->fan_ntiles;
     // split along the chords when the launch is small and the caller gave the scratch for it (a0.fan_scratch);
-    // not with a column share (its columns are not the whole detector), nor when samples are counted
-    a.fan_split = (a0.fan_scratch && !a0.nsamples && p->fan_share_parts == 1) ? fan_parts(p, count) : 1;
+    // not when samples are counted
+    a.fan_split = (a0.fan_scratch && !a0.nsamples) ? fan_parts(p, count) : 1;
     if (a.fan_split == 1) a.fan_scratch = nullptr;
     PAX_REQUIRE(a.fan_order, "pax_ax: the fan-plane projector was not configured for this plan");
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");

@@ -330,6 +330,11 @@ __device__ __forceinline__ void mc_st4(float *p, float4 v)
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void mc_red4(float *p, float4 v)
+{
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void mc_st1(float *p, float v)
 {
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
@@ -400,23 +405,46 @@ struct PeerDst {
 };
 
 template <bool MC>
-__global__ void __launch_bounds__(256) k_bcast_chunks(const char *__restrict__ src, char *dst_mc, const PeerDst peers,
-                                                      int world, size_t chunk16, long first, long stride)
+__global__ void __launch_bounds__(256) k_bcast_chunks(const char *__restrict__ src, long src_first, char *dst_mc,
+                                                      const PeerDst peers, int world, size_t chunk16, long first,
+                                                      long stride, int add)
 {
     // blockIdx.y = chunk, grid-stride over its 16-byte units: a warp moves 512 contiguous bytes per instruction
     const size_t off = ((size_t)first + (size_t)blockIdx.y * (size_t)stride) * chunk16 * 16;
+    const size_t soff = src_first < 0 ? off : ((size_t)src_first + (size_t)blockIdx.y * (size_t)stride) * chunk16 * 16;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunk16; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = *reinterpret_cast<const float4 *>(src + off + i * 16);
+        const float4 v = *reinterpret_cast<const float4 *>(src + soff + i * 16);
         if (MC) {
-            mc_st4(reinterpret_cast<float *>(dst_mc + off + i * 16), v);
+            if (add) mc_red4(reinterpret_cast<float *>(dst_mc + off + i * 16), v);
+            else mc_st4(reinterpret_cast<float *>(dst_mc + off + i * 16), v);
         } else {
-            for (int r = 0; r < world; ++r) *reinterpret_cast<float4 *>(peers.p[r] + off + i * 16) = v;
+            for (int r = 0; r < world; ++r) {
+                float *d = reinterpret_cast<float *>(peers.p[r] + off + i * 16);
+                if (add) { atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w); }
+                else *reinterpret_cast<float4 *>(d) = v;
+            }
         }
     }
 }
 
+extern "C" int pax_bcast_chunks2(const void *src, long src_first_chunk, void *dst_mc, const uint64_t *dst_peers,
+                                 int world, size_t chunk_bytes, long first_chunk, long chunk_stride, long n_chunks,
+                                 int add, void *stream);
+
 extern "C" int pax_bcast_chunks(const void *src_local, void *dst_mc, const uint64_t *dst_peers, int world,
                                 size_t chunk_bytes, long first_chunk, long chunk_stride, long n_chunks, void *stream)
+{
+    return pax_bcast_chunks2(src_local, -1, dst_mc, dst_peers, world, chunk_bytes, first_chunk, chunk_stride, n_chunks,
+                             0, stream);
+}
+
+// The general form: the chunks are read from `src` starting at chunk src_first_chunk (-1: at the same place as in
+// the destination, i.e. src is this rank's copy of the symmetric buffer), and with add != 0 they are ADDED to what
+// every rank's buffer holds (multimem.red: the switch does the adds; ranks that each hold some columns of one
+// projection merge them this way into a zeroed slot).
+extern "C" int pax_bcast_chunks2(const void *src_local, long src_first_chunk, void *dst_mc, const uint64_t *dst_peers,
+                                 int world, size_t chunk_bytes, long first_chunk, long chunk_stride, long n_chunks,
+                                 int add, void *stream)
 {
     PAX_REQUIRE(src_local && (dst_mc || dst_peers), "pax_bcast_chunks: NULL argument");
     PAX_REQUIRE(world >= 1 && world <= PAX_MAX_PEERS, "pax_bcast_chunks: world %d", world);
@@ -431,12 +459,12 @@ extern "C" int pax_bcast_chunks(const void *src_local, void *dst_mc, const uint6
     dim3 grid(bx, (unsigned)n_chunks);
     cudaStream_t st = (cudaStream_t)stream;
     if (dst_mc)
-        k_bcast_chunks<true><<<grid, 256, 0, st>>>(reinterpret_cast<const char *>(src_local),
+        k_bcast_chunks<true><<<grid, 256, 0, st>>>(reinterpret_cast<const char *>(src_local), src_first_chunk,
                                                    reinterpret_cast<char *>(dst_mc), peers, world, c16, first_chunk,
-                                                   chunk_stride);
+                                                   chunk_stride, add);
     else
-        k_bcast_chunks<false><<<grid, 256, 0, st>>>(reinterpret_cast<const char *>(src_local), nullptr, peers, world,
-                                                    c16, first_chunk, chunk_stride);
+        k_bcast_chunks<false><<<grid, 256, 0, st>>>(reinterpret_cast<const char *>(src_local), src_first_chunk, nullptr,
+                                                    peers, world, c16, first_chunk, chunk_stride, add);
     PAX_CHECK_CUDA(cudaGetLastError());
     return PAX_OK;
 }

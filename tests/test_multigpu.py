@@ -28,7 +28,7 @@ def _worker(rank, world, port, q, shard):
     from physics_arx_b200.phantom import artifact_volume, lung_phantom, make_geometry
     from physics_arx_b200.pipeline import SCBCTPipeline
     geo = make_geometry((16, 40, 40), (10.0, 6.0, 6.0), (40, 72), (6.0, 4.0), off_detector=(0.0, -30.0))
-    if shard == "tiles":                    # fine rows over thick slices: AUTO picks the fan-plane projector, and
+    if shard in ("tiles", "gather_tiles"):  # fine rows over thick slices: AUTO picks the fan-plane projector, and
         # the bands of a grid become shares of its column tiles (OSSARTState.tiles)
         geo = make_geometry((16, 40, 40), (10.0, 4.0, 4.0), (160, 72), (1.5, 4.0), off_detector=(0.0, -30.0))
     angles = np.linspace(0, 2 * np.pi, 23)
@@ -46,6 +46,9 @@ def _worker(rank, world, port, q, shard):
     elif shard == "tiles":
         del os.environ["PAX_FUSED_UPDATE"]
         shard, want = (1, world), "fused"
+    elif shard == "gather_tiles":           # the gather scheme where the auto grid has column-tile shares (23 angles in
+        del os.environ["PAX_FUSED_UPDATE"]  # blocks of 5 share no factor with the rank count: 1 x world)
+        shard, want = "auto", "gather"
     elif shard == "default":                # what a caller gets: the gather scheme (residual all-gather, row-owned
         del os.environ["PAX_FUSED_UPDATE"]  # backprojection + update, row broadcast)
         shard, want = "auto", "gather"
@@ -60,7 +63,9 @@ def _worker(rank, world, port, q, shard):
     coll = "nccl" if pipe.st.fused is None else pipe.st.fused["kind"]
     if want == "gather":
         assert pipe.st.scheme == "gather", getattr(pipe.st, "gather_error", "")
-        coll = "gather, " + pipe.st.gsym["kind"]
+        coll = "gather, " + pipe.st.gsym["kind"] + f", grid {pipe.st.grid}, tiles {pipe.st.tiles}"
+        if pipe.plan.projector == "fan":
+            assert pipe.st.grid == (1, world) and pipe.st.tiles == (dist.get_rank(), world)
     elif want == "fused":
         assert pipe.st.fused is not None, getattr(pipe.st, "fused_error", "")
     else:
@@ -83,7 +88,7 @@ def _worker(rank, world, port, q, shard):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("shard", ["angles", "rows", "cols", "grid", "p2p", "fused", "default", "tiles"])
+@pytest.mark.parametrize("shard", ["angles", "rows", "cols", "grid", "p2p", "fused", "default", "tiles", "gather_tiles"])
 def test_sharded_pipeline_equals_single_gpu(shard):
     import torch
     n = torch.cuda.device_count()
