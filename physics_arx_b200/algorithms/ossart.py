@@ -95,8 +95,12 @@ class OSSARTState:
         # the ranks form an A x R grid: the angles of every subset over A groups, the detector over R bands
         # (of columns, or of rows with shard='rows')
         self.grid = choose_shard(self.blocks, self.world, shard) if self.world > 1 else (1, 1)
-        if self.scheme == "gather" and self.plan_full.projector != "fan":
-            self.grid = (self.world, 1)          # column-tile shares need the fan projector: angles only
+        if self.scheme == "gather" and (self.plan_full.projector != "fan" or os_environ("PAX_MGPU_GRID") != "auto"):
+            # Angles only.  (PAX_MGPU_GRID=auto lets the ranks of an angle group take shares of the detector's
+            # column tiles instead -- equal work for every rank where the angles do not divide evenly, their
+            # residual columns ADDED into the symmetric set.  Measured at C2 on 8 GPUs: 4 x 2 shares 0.879 s per
+            # volume, 8 x 1 with its 2-or-3-angle imbalance 0.860 s: the adds cost what the balance gains.)
+            self.grid = (self.world, 1)
         A, R = self.grid
         self.axis = band_axis(shard)
         self.shard = "angles" if R == 1 else (self.axis if A == 1 else "grid")

@@ -48,6 +48,7 @@ def _worker(rank, world, port, q, shard):
         shard, want = (1, world), "fused"
     elif shard == "gather_tiles":           # the gather scheme where the auto grid has column-tile shares (23 angles in
         del os.environ["PAX_FUSED_UPDATE"]  # blocks of 5 share no factor with the rank count: 1 x world)
+        os.environ["PAX_MGPU_GRID"] = "auto"
         shard, want = "auto", "gather"
     elif shard == "default":                # what a caller gets: the gather scheme (residual all-gather, row-owned
         del os.environ["PAX_FUSED_UPDATE"]  # backprojection + update, row broadcast)
@@ -64,8 +65,11 @@ def _worker(rank, world, port, q, shard):
     if want == "gather":
         assert pipe.st.scheme == "gather", getattr(pipe.st, "gather_error", "")
         coll = "gather, " + pipe.st.gsym["kind"] + f", grid {pipe.st.grid}, tiles {pipe.st.tiles}"
-        if pipe.plan.projector == "fan":
-            assert pipe.st.grid == (1, world) and pipe.st.tiles == (dist.get_rank(), world)
+        if os.environ.get("PAX_MGPU_GRID") == "auto":
+            assert pipe.plan.projector == "fan" and pipe.st.grid == (1, world)
+            assert pipe.st.tiles == (dist.get_rank(), world)
+        else:
+            assert pipe.st.grid == (world, 1) and pipe.st.tiles is None
     elif want == "fused":
         assert pipe.st.fused is not None, getattr(pipe.st, "fused_error", "")
     else:
