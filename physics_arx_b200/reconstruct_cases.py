@@ -51,7 +51,11 @@ def list_cases(in_dir):
 
 def pCT_CBCT_reconstruction(in_dir, niter=30, blocksize=20, n_angles=500, Poisson=1e8,
                             Gaussian=np.array([0, 4]), seed=0, half_fan=False, save_projections=True,
-                            verbose=True):
+                            verbose=True, w_variant="matlab", v_variant="A"):
+    """The reference script's loop (module docstring).  ``w_variant`` / ``v_variant`` choose between the W / V
+    definitions of TIGRE's builds (the script's TIGRE checkout is un-pinned): the defaults are
+    current upstream's (MATLAB ``computeW``; V from ``Atb(ones)``, the variant half-fan needs), ``'python2021'``
+    / ``'B'`` are those of the mid-2021 Python package the script's date points at."""
     import torch
 
     from . import Ax
@@ -78,7 +82,8 @@ def pCT_CBCT_reconstruction(in_dir, niter=30, blocksize=20, n_angles=500, Poisso
                      projection=noise_projections.cpu().numpy())
         out_dir = os.path.join(in_dir, patient, 'Recons')
         os.makedirs(os.path.join(out_dir, 'QualMeasure'), exist_ok=True)
-        rec = ossart(noise_projections, geo, angles, niter, blocksize=blocksize, gpuids=gpuids)
+        rec = ossart(noise_projections, geo, angles, niter, blocksize=blocksize, gpuids=gpuids,
+                     w_variant=w_variant, v_variant=v_variant)
         filename = os.path.join(out_dir, patient + '_pCT_OSSART_' + caseID + '.nrrd')
         write_nrrd(filename, rec.cpu().numpy(), img.GetSpacing(), img.GetOrigin(), img.direction, img.space)
         done.append(filename)
