@@ -42,6 +42,7 @@
 #define FAN_QCAP 96             // crossing events served per round
 #define FAN_MAXROWS 1024        // detector rows one warp walks
 #define FAN_EPMAX 256           // most steps per epoch
+#define FAN_BW 16               // columns per block of the queued launch
 
 template <int CW>
 struct __align__(16) FanSmem {
@@ -59,6 +60,7 @@ struct __align__(16) FanSmem {
     unsigned char lane_seg[32];
     unsigned starts[FAN_MAXROWS / 32];         // bit r of word w: row 32w+r starts a run of equal n
     int run_n[32];                             // n of the column's first 32 runs (more: recomputed on the fly)
+    int sched[4];                              // k_ax_fan_queued: the queue this warp takes from, queues found empty
 };
 
 // first row after `cur` that starts a new run (or nRows)
@@ -126,25 +128,13 @@ __device__ __forceinline__ float fan_rcp_step(int i)
     return i > 0 ? __frcp_rn((float)i) : 2.0f;             // decreasing in i, finite at the source
 }
 
-template <int CW, int NWARPS, int MINB, int MODE>
-__global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
+// One detector column (angle ia of the launch, column u, row band `by`, chord part `bz` of a.fan_split), walked by
+// the calling warp alone: `sm` and `rsum` are the warp's own shared memory.
+template <int CW, int MODE>
+__device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, float *rsum, const int lane, const int u,
+                                           const int ia, const int by, const int bz)
 {
-    extern __shared__ __align__(16) unsigned char fan_smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rows_pad = (a.fan_rows + 3) & ~3;
-    const size_t per_warp = sizeof(FanSmem<CW>) + (size_t)rows_pad * sizeof(float);
-    FanSmem<CW> &sm = *reinterpret_cast<FanSmem<CW> *>(fan_smem_raw + (size_t)warp * per_warp);
-    float *rsum = reinterpret_cast<float *>(&sm + 1);             // running line integral of every row of the band
-
-    // CTA order: angle fastest, then the column tile.  The angles of a launch are a few degrees apart, so at any
-    // time the resident CTAs walk chords through one narrow bow-tie of the volume, which stays in L2 while the
-    // bow-tie sweeps across (column-tile-fastest order re-read the volume from DRAM once per angle)
-    // Column tiles in order of decreasing chord length (a.fan_order): a warp walks its column alone, so a long
-    // chord that starts in the last wave of CTAs would keep the launch waiting with most of the SMs idle
-    const int u = a.fan_order[blockIdx.x / a.fan_count] * NWARPS + warp;
-    if (u >= a.nu) return;                                        // warps are independent: no CTA barriers below
-    const int ia = blockIdx.x % a.fan_count;
-    const int V0 = blockIdx.y * a.fan_rows;
+    const int V0 = by * a.fan_rows;
     const int nRows = min(a.fan_rows, a.nv - V0);
     const AngleDev &A = a.angles[a.first + ia];
     const double sx = A.sx, sy = A.sy, sz = A.sz;
@@ -198,7 +188,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
         // a launch too small to fill the GPU more than a few times over is cut into `fan_split` parts along the
         // chord (whole epochs: their sums are independent), one warp each; k_fan_finish adds the parts up
         const int nep = (Emax - Emin) / EP + 1;
-        const int mA = nep * (int)blockIdx.z / a.fan_split, mB = nep * ((int)blockIdx.z + 1) / a.fan_split;
+        const int mA = nep * bz / a.fan_split, mB = nep * (bz + 1) / a.fan_split;
 #pragma unroll 1
         for (int e0 = Emin + mA * EP; e0 < Emin + mB * EP; e0 += EP) {
             const int e1 = min(e0 + EP - 1, Emax);
@@ -494,7 +484,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     __syncwarp();
 
     if (a.fan_split > 1) {                                        // raw sums of my part; k_fan_finish does the rest
-        float *dst = a.fan_scratch + (((size_t)blockIdx.z * a.fan_count + ia) * a.nv + V0) * a.nu + u;
+        float *dst = a.fan_scratch + (((size_t)bz * a.fan_count + ia) * a.nv + V0) * a.nu + u;
         for (int r = lane; r < nRows; r += 32) dst[(size_t)r * a.nu] = rsum[r];
         return;
     }
@@ -557,6 +547,73 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     if (MODE == PAX_AX_RESIDUAL && a.sumsq) {
         for (int o = 16; o; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
         if (lane == 0) atomicAdd(a.sumsq, (double)r2);
+    }
+}
+
+template <int CW, int NWARPS, int MINB, int MODE>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
+{
+    extern __shared__ __align__(16) unsigned char fan_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows_pad = (a.fan_rows + 3) & ~3;
+    const size_t per_warp = sizeof(FanSmem<CW>) + (size_t)rows_pad * sizeof(float);
+    FanSmem<CW> &sm = *reinterpret_cast<FanSmem<CW> *>(fan_smem_raw + (size_t)warp * per_warp);
+    float *rsum = reinterpret_cast<float *>(&sm + 1);             // running line integral of every row of the band
+
+    // CTA order: angle fastest, then the column tile.  The angles of a launch are a few degrees apart, so at any
+    // time the resident CTAs walk chords through one narrow bow-tie of the volume, which stays in L2 while the
+    // bow-tie sweeps across (column-tile-fastest order re-read the volume from DRAM once per angle)
+    // Column tiles in order of decreasing chord length (a.fan_order): a warp walks its column alone, so a long
+    // chord that starts in the last wave of CTAs would keep the launch waiting with most of the SMs idle
+    const int u = a.fan_order[blockIdx.x / a.fan_count] * NWARPS + warp;
+    if (u >= a.nu) return;                                        // warps are independent: no CTA barriers
+    fan_column<CW, MODE>(a, sm, rsum, lane, u, blockIdx.x % a.fan_count, blockIdx.y, blockIdx.z);
+}
+
+// The same walk with the columns handed out at run time, one per WARP: every SM has a queue of blocks of FAN_BW
+// adjacent columns of one angle (blocks in the order above, dealt round-robin to the SMs), and a warp that is done
+// takes the next column of its SM's queue -- the 16 warps resident on an SM walk neighbouring chords at about the
+// same time and share the cells they read through L1.  A warp whose queue is empty takes from the other SMs'.
+template <int CW, int NWARPS, int MINB, int MODE>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_queued(const AxArgs a)
+{
+    extern __shared__ __align__(16) unsigned char fan_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows_pad = (a.fan_rows + 3) & ~3;
+    const size_t per_warp = sizeof(FanSmem<CW>) + (size_t)rows_pad * sizeof(float);
+    FanSmem<CW> &sm = *reinterpret_cast<FanSmem<CW> *>(fan_smem_raw + (size_t)warp * per_warp);
+    float *rsum = reinterpret_cast<float *>(&sm + 1);
+    const int nq = a.fan_nqueue, nblk = a.fan_nblock;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (lane == 0) { sm.sched[0] = (int)(smid % (unsigned)nq); sm.sched[1] = 0; }
+    __syncwarp();
+#pragma unroll 1
+    for (;;) {
+        int idx = -1, q = 0;
+        if (lane == 0) {
+            q = sm.sched[0];
+            int tried = sm.sched[1];
+            while (tried < nq) {
+                const int tot = q < nblk ? ((nblk - q + nq - 1) / nq) * FAN_BW : 0;
+                if (*(volatile int *)(a.fan_queue + q) < tot) {
+                    const int i = atomicAdd(a.fan_queue + q, 1);
+                    if (i < tot) { idx = i; break; }
+                }
+                q = q + 1 == nq ? 0 : q + 1;
+                ++tried;
+            }
+            sm.sched[0] = q; sm.sched[1] = tried;
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (idx < 0) break;
+        int blk = q + nq * (idx / FAN_BW);                        // the block, in launch order: angle fastest
+        const int ia = blk % a.fan_count;
+        blk /= a.fan_count;
+        const int u = a.fan_order[blk % a.fan_ntiles] * FAN_BW + idx % FAN_BW;
+        if (u < a.nu) fan_column<CW, MODE>(a, sm, rsum, lane, u, ia, blk / a.fan_ntiles, 0);
+        __syncwarp();
     }
 }
 
@@ -646,6 +703,14 @@ static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
     b.fan_count = count;
     dim3 grid(a.fan_ntiles * count, pax_cdiv(a.nv, a.fan_rows), a.fan_split);
     if (a.fan_ntiles == 0) return PAX_OK;
+    if (a.fan_queue) {
+        PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan_queued<CW, NWARPS, MINB, MODE>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        b.fan_nblock = a.fan_ntiles * count * (int)grid.y;
+        PAX_CHECK_CUDA(cudaMemsetAsync(a.fan_queue, 0, sizeof(int) * a.fan_nqueue, st));
+        k_ax_fan_queued<CW, NWARPS, MINB, MODE><<<a.fan_nqueue * MINB, NWARPS * 32, smem, st>>>(b);
+        return PAX_OK;
+    }
     k_ax_fan<CW, NWARPS, MINB, MODE><<<grid, NWARPS * 32, smem, st>>>(b);
     if (a.fan_split > 1) {
         const size_t n = (size_t)count * a.nv * a.fan_ntiles * NWARPS;
@@ -674,6 +739,14 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     // not when samples are counted
     a.fan_split = (a0.fan_scratch && !a0.nsamples) ? fan_parts(p, count) : 1;
     if (a.fan_split == 1) a.fan_scratch = nullptr;
+    if (p->fan_queued && a.fan_split == 1 && p->fan_share_parts == 1 && !p->h_fan_order_q.empty()) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+        a.fan_queue = p->d_fan_queue;
+        a.fan_nqueue = std::min(sms, PAX_FAN_MAXQ);
+        a.fan_order = p->d_fan_order_q;
+        a.fan_ntiles = (int)p->h_fan_order_q.size();
+    }
     PAX_REQUIRE(a.fan_order, "pax_ax: the fan-plane projector was not configured for this plan");
     PAX_REQUIRE(((uintptr_t)a.vol0 & 15) == 0, "pax_ax: resident volume must be 16-byte aligned");
     PAX_REQUIRE(p->vol_elems < ((size_t)1 << 30), "pax_ax: resident volume too large for the fan-plane kernel");
@@ -722,8 +795,8 @@ int pax_fan_configure(PaxPlan *p)
     p->fan_rows = (g.nDetecV + tiles - 1) / tiles;
     // launch order of the column tiles: longest chords first (mean over a few of the plan's angles of the in-plane
     // chord through the volume's box, summed over the tile's columns)
-    {
-        const int ntile = (g.nDetecU + nw - 1) / nw;
+    auto order_of = [&](int width, std::vector<int> &order) {
+        const int ntile = (g.nDetecU + width - 1) / width;
         std::vector<double> cost(ntile, 0.0);
         const int na = (int)p->h_angles.size(), nsamp = std::min(na, 8);
         for (int s = 0; s < nsamp; ++s) {
@@ -739,14 +812,16 @@ int pax_fan_configure(PaxPlan *p)
                 if (dy == 0.0) hit = hit && A.sy >= lo && A.sy < hy;
                 else { const double a0 = (lo - A.sy) / dy, a1 = (hy - A.sy) / dy;
                        t0 = std::fmax(t0, std::fmin(a0, a1)); t1 = std::fmin(t1, std::fmax(a0, a1)); }
-                if (hit && t1 > t0) cost[u / nw] += (t1 - t0) * std::sqrt(dx * dx + dy * dy);
+                if (hit && t1 > t0) cost[u / width] += (t1 - t0) * std::sqrt(dx * dx + dy * dy);
             }
         }
-        p->h_fan_order.resize(ntile);
-        for (int t = 0; t < ntile; ++t) p->h_fan_order[t] = t;
-        std::stable_sort(p->h_fan_order.begin(), p->h_fan_order.end(),
-                         [&](int a_, int b_) { return cost[a_] > cost[b_]; });
-    }
+        order.resize(ntile);
+        for (int t = 0; t < ntile; ++t) order[t] = t;
+        std::stable_sort(order.begin(), order.end(), [&](int a_, int b_) { return cost[a_] > cost[b_]; });
+    };
+    order_of(nw, p->h_fan_order);
+    order_of(FAN_BW, p->h_fan_order_q);
+    p->fan_queued = ((e = getenv("PAX_FAN_QUEUED")) && atoi(e) == 0) ? 0 : 1;                      // tuning hook
     // AUTO's criteria (pax_plan_projector, pax_plan_fan_info): how many detector rows fit the 32 lanes of a warp
     // over one epoch in the worst case, and how long the runs of equal n are (what the sharing is worth)
     {

@@ -50,7 +50,13 @@ struct PaxPlan {
     int *d_fan_order;               // the tiles this plan's launches walk (all of them, or its share)
     int fan_ntiles;                 // how many
     int fan_share_part, fan_share_parts;   // pax_plan_set_column_share
+    // the queued launch (k_ax_fan_queued): blocks of 16 columns in the same order, and one counter per SM
+    std::vector<int> h_fan_order_q;
+    int *d_fan_order_q;             // inside d_fan_order's allocation
+    int *d_fan_queue;               // PAX_FAN_MAXQ counters, cleared before every queued launch
+    int fan_queued;                 // 1: launches that are not split and own all columns go through the queues
 };
+#define PAX_FAN_MAXQ 256
 
 
 // arguments shared by the two forward-projector kernels (ax.cu ray march, ax_fan.cu fan planes)
@@ -84,6 +90,8 @@ struct AxArgs {
     int fan_split;                // ax_fan.cu: parts the launch is cut into along the chords (1: none)
     float *fan_scratch;           // ax_fan.cu: [fan_split][count][V][U] raw sums of a split launch
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
+    int *fan_queue;               // ax_fan.cu, queued launch: next column of every SM's queue
+    int fan_nqueue, fan_nblock;   // ax_fan.cu, queued launch: queues (SMs) and blocks of 16 columns in the launch
     int *fault;                   // ax_fan.cu: set to 1 if a single row's z range did not fit the lanes (never, by construction)
 };
 

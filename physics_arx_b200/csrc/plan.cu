@@ -99,16 +99,22 @@ extern "C" int pax_plan_create(const PaxGeo *geo, const double *rows, int n, Pax
     cudaMemset(p->d_fault, 0, sizeof(int));
     p->projector = PAX_PROJECTOR_AUTO;
     p->d_fan_order = nullptr;
+    p->d_fan_order_q = nullptr;
+    p->d_fan_queue = nullptr;
     p->fan_share_part = 0;
     p->fan_share_parts = 1;
     pax_fan_configure(p);
     p->fan_ntiles = (int)p->h_fan_order.size();
     if (!p->h_fan_order.empty()) {
         // the fan-plane kernel's column tiles, longest chords first (ax_fan.cu: tail of the last wave)
-        e = cudaMalloc(&p->d_fan_order, sizeof(int) * p->h_fan_order.size());
+        const size_t n4 = p->h_fan_order.size(), nq = p->h_fan_order_q.size();
+        e = cudaMalloc(&p->d_fan_order, sizeof(int) * (n4 + nq + PAX_FAN_MAXQ));
         if (e == cudaSuccess)
-            e = cudaMemcpy(p->d_fan_order, p->h_fan_order.data(), sizeof(int) * p->h_fan_order.size(),
-                           cudaMemcpyHostToDevice);
+            e = cudaMemcpy(p->d_fan_order, p->h_fan_order.data(), sizeof(int) * n4, cudaMemcpyHostToDevice);
+        p->d_fan_order_q = p->d_fan_order + n4;
+        p->d_fan_queue = p->d_fan_order_q + nq;
+        if (e == cudaSuccess && nq)
+            e = cudaMemcpy(p->d_fan_order_q, p->h_fan_order_q.data(), sizeof(int) * nq, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             if (p->d_fan_order) cudaFree(p->d_fan_order);
             cudaFree(p->d_angles);
