@@ -130,11 +130,13 @@ __device__ __forceinline__ float fan_rcp_step(int i)
 
 // One detector column (angle ia of the launch, column u, row band `by`, chord part `bz` of a.fan_split), walked by
 // the calling warp alone: `sm` and `rsum` are the warp's own shared memory.
-template <int CW, int MODE>
+// (QUEUED: band and part come from the warp's shared memory where they are needed, not through registers)
+template <int CW, int MODE, bool QUEUED>
 __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, float *rsum, const int lane, const int u,
-                                           const int ia, const int by, const int bz)
+                                           const int ia)
 {
-    const int V0 = by * a.fan_rows;
+    auto part_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[3] : (int)blockIdx.z; };
+    const int V0 = (QUEUED ? ((volatile int *)sm.sched)[2] : (int)blockIdx.y) * a.fan_rows;
     const int nRows = min(a.fan_rows, a.nv - V0);
     const AngleDev &A = a.angles[a.first + ia];
     const double sx = A.sx, sy = A.sy, sz = A.sz;
@@ -188,6 +190,7 @@ __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, flo
         // a launch too small to fill the GPU more than a few times over is cut into `fan_split` parts along the
         // chord (whole epochs: their sums are independent), one warp each; k_fan_finish adds the parts up
         const int nep = (Emax - Emin) / EP + 1;
+        const int bz = part_of();
         const int mA = nep * bz / a.fan_split, mB = nep * (bz + 1) / a.fan_split;
 #pragma unroll 1
         for (int e0 = Emin + mA * EP; e0 < Emin + mB * EP; e0 += EP) {
@@ -484,7 +487,7 @@ __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, flo
     __syncwarp();
 
     if (a.fan_split > 1) {                                        // raw sums of my part; k_fan_finish does the rest
-        float *dst = a.fan_scratch + (((size_t)bz * a.fan_count + ia) * a.nv + V0) * a.nu + u;
+        float *dst = a.fan_scratch + (((size_t)part_of() * a.fan_count + ia) * a.nv + V0) * a.nu + u;
         for (int r = lane; r < nRows; r += 32) dst[(size_t)r * a.nu] = rsum[r];
         return;
     }
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     // chord that starts in the last wave of CTAs would keep the launch waiting with most of the SMs idle
     const int u = a.fan_order[blockIdx.x / a.fan_count] * NWARPS + warp;
     if (u >= a.nu) return;                                        // warps are independent: no CTA barriers
-    fan_column<CW, MODE>(a, sm, rsum, lane, u, blockIdx.x % a.fan_count, blockIdx.y, blockIdx.z);
+    fan_column<CW, MODE, false>(a, sm, rsum, lane, u, blockIdx.x % a.fan_count);
 }
 
 // The same walk with the columns handed out at run time, one per WARP: every SM has a queue of blocks of FAN_BW
@@ -584,6 +587,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_queued(const AxArg
     FanSmem<CW> &sm = *reinterpret_cast<FanSmem<CW> *>(fan_smem_raw + (size_t)warp * per_warp);
     float *rsum = reinterpret_cast<float *>(&sm + 1);
     const int nq = a.fan_nqueue, nblk = a.fan_nblock;
+    constexpr int bw = FAN_BW;
     unsigned smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     if (lane == 0) { sm.sched[0] = (int)(smid % (unsigned)nq); sm.sched[1] = 0; }
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_queued(const AxArg
             q = sm.sched[0];
             int tried = sm.sched[1];
             while (tried < nq) {
-                const int tot = q < nblk ? ((nblk - q + nq - 1) / nq) * FAN_BW : 0;
+                const int tot = q < nblk ? ((nblk - q + nq - 1) / nq) * bw : 0;
                 if (*(volatile int *)(a.fan_queue + q) < tot) {
                     const int i = atomicAdd(a.fan_queue + q, 1);
                     if (i < tot) { idx = i; break; }
@@ -608,11 +612,16 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_queued(const AxArg
         idx = __shfl_sync(0xffffffffu, idx, 0);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (idx < 0) break;
-        int blk = q + nq * (idx / FAN_BW);                        // the block, in launch order: angle fastest
+        int blk = q + nq * (idx / bw);                        // the block, in launch order: angle fastest
         const int ia = blk % a.fan_count;
         blk /= a.fan_count;
-        const int u = a.fan_order[blk % a.fan_ntiles] * FAN_BW + idx % FAN_BW;
-        if (u < a.nu) fan_column<CW, MODE>(a, sm, rsum, lane, u, ia, blk / a.fan_ntiles, 0);
+        const int u = a.fan_order[blk % a.fan_ntiles] * bw + idx % bw;
+        if (lane == 0) {                                          // row band fastest, then the part of the chord
+            const int band = blk / a.fan_ntiles;
+            sm.sched[2] = band % a.fan_nband; sm.sched[3] = band / a.fan_nband;
+        }
+        __syncwarp();
+        if (u < a.nu) fan_column<CW, MODE, true>(a, sm, rsum, lane, u, ia);
         __syncwarp();
     }
 }
@@ -706,9 +715,15 @@ static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
     if (a.fan_queue) {
         PAX_CHECK_CUDA(cudaFuncSetAttribute(k_ax_fan_queued<CW, NWARPS, MINB, MODE>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        b.fan_nblock = a.fan_ntiles * count * (int)grid.y;
+        b.fan_nband = (int)grid.y;
+        b.fan_nblock = a.fan_ntiles * count * (int)grid.y * a.fan_split;
         PAX_CHECK_CUDA(cudaMemsetAsync(a.fan_queue, 0, sizeof(int) * a.fan_nqueue, st));
         k_ax_fan_queued<CW, NWARPS, MINB, MODE><<<a.fan_nqueue * MINB, NWARPS * 32, smem, st>>>(b);
+        if (a.fan_split > 1) {
+            const size_t n = (size_t)count * a.nv * a.fan_ntiles * a.fan_bw;
+            const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+            k_fan_finish<MODE><<<blocks, 256, 0, st>>>(b, a.fan_bw);
+        }
         return PAX_OK;
     }
     k_ax_fan<CW, NWARPS, MINB, MODE><<<grid, NWARPS * 32, smem, st>>>(b);
@@ -739,12 +754,13 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     // not when samples are counted
     a.fan_split = (a0.fan_scratch && !a0.nsamples) ? fan_parts(p, count) : 1;
     if (a.fan_split == 1) a.fan_scratch = nullptr;
-    if (p->fan_queued && a.fan_split == 1 && p->fan_share_parts == 1 && !p->h_fan_order_q.empty()) {
+    if (p->fan_queued && p->fan_share_parts == 1 && !p->h_fan_order_q.empty()) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
         a.fan_queue = p->d_fan_queue;
         a.fan_nqueue = std::min(sms, PAX_FAN_MAXQ);
         a.fan_order = p->d_fan_order_q;
+        a.fan_bw = p->fan_bw;
         a.fan_ntiles = (int)p->h_fan_order_q.size();
     }
     PAX_REQUIRE(a.fan_order, "pax_ax: the fan-plane projector was not configured for this plan");
@@ -820,7 +836,8 @@ int pax_fan_configure(PaxPlan *p)
         std::stable_sort(order.begin(), order.end(), [&](int a_, int b_) { return cost[a_] > cost[b_]; });
     };
     order_of(nw, p->h_fan_order);
-    order_of(FAN_BW, p->h_fan_order_q);
+    p->fan_bw = FAN_BW;         // (4 .. 32 columns per block measured within 1.5 % of each other)
+    order_of(p->fan_bw, p->h_fan_order_q);
     p->fan_queued = ((e = getenv("PAX_FAN_QUEUED")) && atoi(e) == 0) ? 0 : 1;                      // tuning hook
     // AUTO's criteria (pax_plan_projector, pax_plan_fan_info): how many detector rows fit the 32 lanes of a warp
     // over one epoch in the worst case, and how long the runs of equal n are (what the sharing is worth)

@@ -54,7 +54,8 @@ struct PaxPlan {
     std::vector<int> h_fan_order_q;
     int *d_fan_order_q;             // inside d_fan_order's allocation
     int *d_fan_queue;               // PAX_FAN_MAXQ counters, cleared before every queued launch
-    int fan_queued;                 // 1: launches that are not split and own all columns go through the queues
+    int fan_bw;                     // columns per block
+    int fan_queued;                 // 1: launches that own all columns go through the queues
 };
 #define PAX_FAN_MAXQ 256
 
@@ -91,7 +92,9 @@ struct AxArgs {
     float *fan_scratch;           // ax_fan.cu: [fan_split][count][V][U] raw sums of a split launch
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
     int *fan_queue;               // ax_fan.cu, queued launch: next column of every SM's queue
-    int fan_nqueue, fan_nblock;   // ax_fan.cu, queued launch: queues (SMs) and blocks of 16 columns in the launch
+    int fan_bw;                   // ax_fan.cu, queued launch: columns per block
+    int fan_nqueue, fan_nblock;   // ax_fan.cu, queued launch: queues (SMs) and blocks of columns in the launch
+    int fan_nband;                // ax_fan.cu, queued launch: row bands (grid.y of the plain launch)
     int *fault;                   // ax_fan.cu: set to 1 if a single row's z range did not fit the lanes (never, by construction)
 };
 
