@@ -60,7 +60,7 @@ struct __align__(16) FanSmem {
     unsigned char lane_seg[32];
     unsigned starts[FAN_MAXROWS / 32];         // bit r of word w: row 32w+r starts a run of equal n
     int run_n[32];                             // n of the column's first 32 runs (more: recomputed on the fly)
-    int sched[4];                              // k_ax_fan_queued: the queue this warp takes from, queues found empty
+    int sched[8];                              // k_ax_fan_queued: the queue this warp takes from, queues found empty
 };
 
 // first row after `cur` that starts a new run (or nRows)
@@ -136,6 +136,8 @@ __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, flo
                                            const int ia)
 {
     auto part_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[3] : (int)blockIdx.z; };
+    auto col_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[4] : u; };
+    auto ang_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[5] : ia; };
     const int V0 = (QUEUED ? ((volatile int *)sm.sched)[2] : (int)blockIdx.y) * a.fan_rows;
     const int nRows = min(a.fan_rows, a.nv - V0);
     const AngleDev &A = a.angles[a.first + ia];
@@ -487,12 +489,13 @@ __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, flo
     __syncwarp();
 
     if (a.fan_split > 1) {                                        // raw sums of my part; k_fan_finish does the rest
-        float *dst = a.fan_scratch + (((size_t)part_of() * a.fan_count + ia) * a.nv + V0) * a.nu + u;
+        float *dst = a.fan_scratch + (((size_t)part_of() * a.fan_count + ang_of()) * a.nv + V0) * a.nu + col_of();
         for (int r = lane; r < nRows; r += 32) dst[(size_t)r * a.nu] = rsum[r];
         return;
     }
     // ---- epilogue, run by run (the step length in mm depends on n).  The warps of the CTA own adjacent columns and
     // fill one 32-byte sector of every row between them; L2 merges the partial writes.
+    const int ue = col_of(), iae = ang_of();
     int cur = 0;
     while (cur < nRows) {
         const int e = fan_next_start(sm.starts, cur, nRows);
@@ -508,7 +511,7 @@ __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, flo
         }
         for (int r = cur + lane; r < e; r += 32) {
             const int v = V0 + r;
-            const size_t o = ((size_t)ia * a.nv + v) * a.nu + u;
+            const size_t o = ((size_t)iae * a.nv + v) * a.nu + ue;
             const double mx = ddx * a.dX, my = ddy * a.dY, mz = (dz0 + (double)r * vz) * rn * a.dZ;
             const float p0 = rsum[r] * (float)sqrt(mx * mx + my * my + mz * mz);
             if (a.nsamples) {                                     // exact count of the samples inside the open box
@@ -522,12 +525,12 @@ __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, flo
             }
             if (MODE == PAX_AX_PLAIN) {
                 float val = a.a0 * p0;
-                if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, u, v, a.whx, a.why, a.whz), val);
+                if (a.c != 0.f) val = fmaf(a.c, pax_ray_chord(A, ue, v, a.whx, a.why, a.whz), val);
                 if (a.accumulate) val += a.out[o];
                 a.out[o] = val;
                 mymax = fmaxf(mymax, val);
             } else {
-                const float L = pax_ray_chord(A, u, v, a.whx, a.why, a.whz);
+                const float L = pax_ray_chord(A, ue, v, a.whx, a.why, a.whz);
                 const float w = L > a.wthr ? 1.f / L : 0.f;
                 const float r_ = __ldg(a.b + o) - p0;
                 r2 = fmaf(r_, r_, r2);
@@ -553,6 +556,18 @@ __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, flo
     }
 }
 
+// Launch order of the (column tile, angle) pairs of a launch: angle fastest, then the column tile.  The angles of a
+// launch are a few degrees apart, so at any time the resident warps walk chords through one narrow bow-tie of the
+// volume, which stays in L2 while the bow-tie sweeps across (column-tile-fastest order re-read the volume from
+// DRAM once per angle; the 656 angles of C2 in one launch take 146 ms, 20 at a time 153 ms).  Column tiles in
+// order of decreasing chord length (a.fan_order): a warp walks its column alone, so a long chord that starts late
+// would keep the launch waiting with most of the SMs idle.
+__device__ __forceinline__ void fan_decode(int p, int count, int &ti, int &ia)
+{
+    ti = p / count;
+    ia = p - ti * count;
+}
+
 template <int CW, int NWARPS, int MINB, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
 {
@@ -563,14 +578,11 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     FanSmem<CW> &sm = *reinterpret_cast<FanSmem<CW> *>(fan_smem_raw + (size_t)warp * per_warp);
     float *rsum = reinterpret_cast<float *>(&sm + 1);             // running line integral of every row of the band
 
-    // CTA order: angle fastest, then the column tile.  The angles of a launch are a few degrees apart, so at any
-    // time the resident CTAs walk chords through one narrow bow-tie of the volume, which stays in L2 while the
-    // bow-tie sweeps across (column-tile-fastest order re-read the volume from DRAM once per angle)
-    // Column tiles in order of decreasing chord length (a.fan_order): a warp walks its column alone, so a long
-    // chord that starts in the last wave of CTAs would keep the launch waiting with most of the SMs idle
-    const int u = a.fan_order[blockIdx.x / a.fan_count] * NWARPS + warp;
+    int ti, ia;
+    fan_decode((int)blockIdx.x, a.fan_count, ti, ia);
+    const int u = a.fan_order[ti] * NWARPS + warp;
     if (u >= a.nu) return;                                        // warps are independent: no CTA barriers
-    fan_column<CW, MODE, false>(a, sm, rsum, lane, u, blockIdx.x % a.fan_count);
+    fan_column<CW, MODE, false>(a, sm, rsum, lane, u, ia);
 }
 
 // The same walk with the columns handed out at run time, one per WARP: every SM has a queue of blocks of FAN_BW
@@ -612,13 +624,14 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_queued(const AxArg
         idx = __shfl_sync(0xffffffffu, idx, 0);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (idx < 0) break;
-        int blk = q + nq * (idx / bw);                        // the block, in launch order: angle fastest
-        const int ia = blk % a.fan_count;
-        blk /= a.fan_count;
-        const int u = a.fan_order[blk % a.fan_ntiles] * bw + idx % bw;
+        const int blk = q + nq * (idx / bw);                      // the block, in launch order
+        const int per = a.fan_ntiles * a.fan_count, band = blk / per;
+        int ti, ia;
+        fan_decode(blk - band * per, a.fan_count, ti, ia);
+        const int u = a.fan_order[ti] * bw + idx % bw;
         if (lane == 0) {                                          // row band fastest, then the part of the chord
-            const int band = blk / a.fan_ntiles;
             sm.sched[2] = band % a.fan_nband; sm.sched[3] = band / a.fan_nband;
+            sm.sched[4] = u; sm.sched[5] = ia;
         }
         __syncwarp();
         if (u < a.nu) fan_column<CW, MODE, true>(a, sm, rsum, lane, u, ia);
