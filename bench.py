@@ -482,7 +482,7 @@ def main():
             l1 = {"bound": "l1_data_pipe", "achieved": ach / 1e9, "peak": l1_peak / 1e9, "unit": "Gwavefronts/s",
                   "frac": ach / l1_peak, "wavefronts_per_launch": wavefronts,
                   "peak_source": "1 wavefront per clock and SM x 148 SMs x the SM clock sampled under load",
-                  "source": "profiles/r2_ncu_fan.json (l1tex__data_pipe_lsu_wavefronts)"}
+                  "source": "profiles/r2_ncu_fan_queued.json (l1tex__data_pipe_lsu_wavefronts)"}
         ax_share = float(sum(ax_ms)) / float(t[0].item()) if ax_ms else None
         samples_resid = samples_per_pass * cfg["niter"] * args.steps     # rank 0's residual passes
         line = {

@@ -152,7 +152,9 @@ int pax_vol_axpy(const PaxPlan *plan, float *y_res, const float *x_res, float a,
  * workspace, FAN kernel: optional device scratch of pax_ax_fan_scratch_bytes(plan, count) bytes (0: none
  * wanted).  A launch too small to fill the GPU a few times over -- a rank's few angles in a multi-GPU
  * run -- is then cut into up to four parts along the chords, whose raw sums go to the scratch and are
- * added up by a second, elementwise kernel; NULL keeps the single launch. */
+ * added up by a second, elementwise kernel; NULL keeps the single launch.
+ * Calls on ONE plan must be ordered (one stream, or events between streams): the FAN kernel hands the
+ * detector columns to its warps through counters that belong to the plan. */
 size_t pax_ax_workspace_bytes(const PaxPlan *plan, int n_channels);
 size_t pax_ax_fan_scratch_bytes(const PaxPlan *plan, int count);
 int pax_ax(const PaxPlan *plan, const float *vol_res0, const float *vol_res1, int first, int count,
