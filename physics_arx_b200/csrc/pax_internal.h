@@ -55,7 +55,7 @@ struct PaxPlan {
     int *d_fan_order_q;             // inside d_fan_order's allocation
     int *d_fan_queue;               // PAX_FAN_MAXQ counters, cleared before every queued launch
     int fan_bw;                     // columns per block
-    int fan_queued;                 // 1: launches that own all columns go through the queues
+    int fan_queued;                 // 1: launches that own all columns and are not split go through the queues
 };
 #define PAX_FAN_MAXQ 256
 
