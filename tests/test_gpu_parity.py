@@ -392,3 +392,36 @@ def test_fan_projector_split_along_the_chords(oracle, parts, monkeypatch):
     plan.ax_residual(res, b, 0, len(angles), want)
     assert rel_l2(out.cpu().numpy(), want.cpu().numpy()) <= 1e-5
     assert abs(float(ss.item()) - float(((b - split) ** 2).sum().item())) <= 1e-4 * float(ss.item())
+
+
+@pytest.mark.parametrize("rows", [72, 1100])
+def test_fan_queued_launch_equals_grid_launch(oracle, rows, monkeypatch):
+    """The fan projector hands its columns to the warps at run time from per-SM queues (csrc/ax_fan.cu,
+    k_ax_fan_queued); PAX_FAN_QUEUED=0 at plan creation selects the plain grid launch of the same per-column walk.
+    Both must give the same bits -- also with more detector rows than one warp walks (two row bands), where the
+    queue's blocks carry the band as well."""
+    torch = _torch()
+    from physics_arx_b200.phantom import make_geometry
+    from physics_arx_b200.projector import Plan
+    geo = make_geometry((24, 48, 48), (2.5, 1.0, 1.0), (rows, 72), (150.0 / rows, 1.6), off_detector=(0.0, -20.0))
+    angles = np.linspace(0, 2 * np.pi, 7, endpoint=False) + 0.3
+    rng = np.random.default_rng(17)
+    vol = rng.random(tuple(int(v) for v in geo.nVoxel)).astype(np.float32)
+    out = {}
+    for queued in ("1", "0"):
+        monkeypatch.setenv("PAX_FAN_QUEUED", queued)
+        plan = Plan(geo, angles, projector="fan")
+        res = plan.pack(torch.from_numpy(vol).cuda())
+        ns = torch.zeros(1, dtype=torch.int64, device="cuda")
+        p = plan.ax(res, nsamples=ns)
+        b = (p * 1.05).contiguous()
+        r = torch.empty_like(p)
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        plan.ax_residual(res, b, 0, len(angles), r, sumsq=ss)
+        assert plan.fault() == 0
+        out[queued] = (p.cpu().numpy(), r.cpu().numpy(), int(ns.item()), float(ss.item()))
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    assert out["1"][2] == out["0"][2]
+    assert abs(out["1"][3] - out["0"][3]) <= 1e-9 * out["0"][3]          # (atomic adds in a different order)
+    if rows <= 300:
+        assert rel_l2(out["1"][0], oracle.ax(vol, geo, angles)) <= 2e-6
