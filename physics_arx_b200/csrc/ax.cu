@@ -355,7 +355,7 @@ extern "C" int pax_ax(const PaxPlan *p, const float *vol_res0, const float *vol_
     a.accumulate = 0;
     a.whx = epi->w_half_x; a.why = epi->w_half_y; a.whz = epi->w_half_z; a.wthr = epi->w_thr;
     a.fan_rows = 0; a.fan_epoch = 0; a.fan_count = 0; a.fan_order = nullptr; a.fan_ntiles = 0; a.fan_split = 1;
-    a.fan_queue = nullptr; a.fan_nqueue = 0; a.fan_nblock = 0; a.fan_bw = 0; a.fan_nband = 1;
+    a.fan_queue = nullptr; a.fan_nblock = 0; a.fan_bw = 0; a.fan_nband = 1; a.fan_sms = 0;
     a.fan_scratch = reinterpret_cast<float *>(workspace);      // (fan projector: optional scratch of a split launch)
     cudaStream_t st = (cudaStream_t)stream;
     PAX_REQUIRE(p->fan_share_parts == 1 || pax_plan_projector(p) == PAX_PROJECTOR_FAN,

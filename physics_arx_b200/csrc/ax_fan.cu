@@ -60,7 +60,7 @@ struct __align__(16) FanSmem {
     unsigned char lane_seg[32];
     unsigned starts[FAN_MAXROWS / 32];         // bit r of word w: row 32w+r starts a run of equal n
     int run_n[32];                             // n of the column's first 32 runs (more: recomputed on the fly)
-    int sched[8];                              // k_ax_fan_queued: the queue this warp takes from, queues found empty
+    int sched[4];                              // k_ax_fan_queued: {row band, chord part, column, angle} of the column at hand
 };
 
 // first row after `cur` that starts a new run (or nRows)
@@ -135,10 +135,10 @@ template <int CW, int MODE, bool QUEUED>
 __device__ __forceinline__ void fan_column(const AxArgs &a, FanSmem<CW> &sm, float *rsum, const int lane, const int u,
                                            const int ia)
 {
-    auto part_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[3] : (int)blockIdx.z; };
-    auto col_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[4] : u; };
-    auto ang_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[5] : ia; };
-    const int V0 = (QUEUED ? ((volatile int *)sm.sched)[2] : (int)blockIdx.y) * a.fan_rows;
+    auto part_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[1] : (int)blockIdx.z; };
+    auto col_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[2] : u; };
+    auto ang_of = [&]() { return QUEUED ? ((volatile int *)sm.sched)[3] : ia; };
+    const int V0 = (QUEUED ? ((volatile int *)sm.sched)[0] : (int)blockIdx.y) * a.fan_rows;
     const int nRows = min(a.fan_rows, a.nv - V0);
     const AngleDev &A = a.angles[a.first + ia];
     const double sx = A.sx, sy = A.sy, sz = A.sz;
@@ -585,10 +585,11 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan(const AxArgs a)
     fan_column<CW, MODE, false>(a, sm, rsum, lane, u, ia);
 }
 
-// The same walk with the columns handed out at run time, one per WARP: every SM has a queue of blocks of FAN_BW
-// adjacent columns of one angle (blocks in the order above, dealt round-robin to the SMs), and a warp that is done
-// takes the next column of its SM's queue -- the 16 warps resident on an SM walk neighbouring chords at about the
-// same time and share the cells they read through L1.  A warp whose queue is empty takes from the other SMs'.
+// The same walk with the columns handed out at run time, one per WARP, from one counter over the launch's columns
+// in the order above (blocks of FAN_BW adjacent columns of one angle): a warp that is done takes the next column,
+// so no warp slot waits for the other warps of a CTA and the tail of the launch is balanced column by column.
+// (Per-SM counters with stealing, meant to keep the 16 warps of an SM on neighbouring chords for L1, measured
+// slower: the L1 left beside the tables is smaller than one step's corner columns of 16 warps.)
 template <int CW, int NWARPS, int MINB, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_queued(const AxArgs a)
 {
@@ -598,40 +599,22 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) k_ax_fan_queued(const AxArg
     const size_t per_warp = sizeof(FanSmem<CW>) + (size_t)rows_pad * sizeof(float);
     FanSmem<CW> &sm = *reinterpret_cast<FanSmem<CW> *>(fan_smem_raw + (size_t)warp * per_warp);
     float *rsum = reinterpret_cast<float *>(&sm + 1);
-    const int nq = a.fan_nqueue, nblk = a.fan_nblock;
     constexpr int bw = FAN_BW;
-    unsigned smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (lane == 0) { sm.sched[0] = (int)(smid % (unsigned)nq); sm.sched[1] = 0; }
-    __syncwarp();
+    const int total = a.fan_nblock * bw;
 #pragma unroll 1
     for (;;) {
-        int idx = -1, q = 0;
-        if (lane == 0) {
-            q = sm.sched[0];
-            int tried = sm.sched[1];
-            while (tried < nq) {
-                const int tot = q < nblk ? ((nblk - q + nq - 1) / nq) * bw : 0;
-                if (*(volatile int *)(a.fan_queue + q) < tot) {
-                    const int i = atomicAdd(a.fan_queue + q, 1);
-                    if (i < tot) { idx = i; break; }
-                }
-                q = q + 1 == nq ? 0 : q + 1;
-                ++tried;
-            }
-            sm.sched[0] = q; sm.sched[1] = tried;
-        }
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(a.fan_queue, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (idx < 0) break;
-        const int blk = q + nq * (idx / bw);                      // the block, in launch order
+        if (idx >= total) break;
+        const int blk = idx / bw;                                 // the block, in launch order
         const int per = a.fan_ntiles * a.fan_count, band = blk / per;
         int ti, ia;
         fan_decode(blk - band * per, a.fan_count, ti, ia);
-        const int u = a.fan_order[ti] * bw + idx % bw;
+        const int u = a.fan_order[ti] * bw + (idx - blk * bw);
         if (lane == 0) {                                          // row band fastest, then the part of the chord
-            sm.sched[2] = band % a.fan_nband; sm.sched[3] = band / a.fan_nband;
-            sm.sched[4] = u; sm.sched[5] = ia;
+            sm.sched[0] = band % a.fan_nband; sm.sched[1] = band / a.fan_nband;
+            sm.sched[2] = u; sm.sched[3] = ia;
         }
         __syncwarp();
         if (u < a.nu) fan_column<CW, MODE, true>(a, sm, rsum, lane, u, ia);
@@ -730,8 +713,8 @@ static int fan_launch(const AxArgs &a, int count, cudaStream_t st)
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         b.fan_nband = (int)grid.y;
         b.fan_nblock = a.fan_ntiles * count * (int)grid.y * a.fan_split;
-        PAX_CHECK_CUDA(cudaMemsetAsync(a.fan_queue, 0, sizeof(int) * a.fan_nqueue, st));
-        k_ax_fan_queued<CW, NWARPS, MINB, MODE><<<a.fan_nqueue * MINB, NWARPS * 32, smem, st>>>(b);
+        PAX_CHECK_CUDA(cudaMemsetAsync(a.fan_queue, 0, sizeof(int), st));
+        k_ax_fan_queued<CW, NWARPS, MINB, MODE><<<a.fan_sms * MINB, NWARPS * 32, smem, st>>>(b);
         if (a.fan_split > 1) {
             const size_t n = (size_t)count * a.nv * a.fan_ntiles * a.fan_bw;
             const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
@@ -767,14 +750,13 @@ int pax_ax_fan_launch(const PaxPlan *p, const AxArgs &a0, int mode, int count, c
     // not when samples are counted
     a.fan_split = (a0.fan_scratch && !a0.nsamples) ? fan_parts(p, count) : 1;
     if (a.fan_split == 1) a.fan_scratch = nullptr;
-    // (not for the small launches that are split along the chords: a warp that runs dry scans the other SMs'
-    // counters one after the other, ~0.1 ms at the end of a launch -- 8 GPUs measured 0.90 s per C2 volume with
-    // queues against 0.86 s with the plain grid)
-    if (p->fan_queued && a.fan_split == 1 && p->fan_share_parts == 1 && !p->h_fan_order_q.empty()) {
+    // (the small launches that are split along the chords keep the plain grid: 2 / 3 / 5 angles of C2 take
+    // 0.680 / 0.937 / 1.399 ms on the grid and 0.688 / 0.930 / 1.408 ms from the queue; PAX_FAN_QUEUED=2 queues them too)
+    if (p->fan_queued && (a.fan_split == 1 || p->fan_queued == 2) && p->fan_share_parts == 1 && !p->h_fan_order_q.empty()) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
         a.fan_queue = p->d_fan_queue;
-        a.fan_nqueue = std::min(sms, PAX_FAN_MAXQ);
+        a.fan_sms = sms;
         a.fan_order = p->d_fan_order_q;
         a.fan_bw = p->fan_bw;
         a.fan_ntiles = (int)p->h_fan_order_q.size();
@@ -854,7 +836,7 @@ int pax_fan_configure(PaxPlan *p)
     order_of(nw, p->h_fan_order);
     p->fan_bw = FAN_BW;         // (4 .. 32 columns per block measured within 1.5 % of each other)
     order_of(p->fan_bw, p->h_fan_order_q);
-    p->fan_queued = ((e = getenv("PAX_FAN_QUEUED")) && atoi(e) == 0) ? 0 : 1;                      // tuning hook
+    p->fan_queued = (e = getenv("PAX_FAN_QUEUED")) ? atoi(e) : 1;                      // tuning hook
     // AUTO's criteria (pax_plan_projector, pax_plan_fan_info): how many detector rows fit the 32 lanes of a warp
     // over one epoch in the worst case, and how long the runs of equal n are (what the sharing is worth)
     {

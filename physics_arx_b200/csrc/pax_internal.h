@@ -50,14 +50,14 @@ struct PaxPlan {
     int *d_fan_order;               // the tiles this plan's launches walk (all of them, or its share)
     int fan_ntiles;                 // how many
     int fan_share_part, fan_share_parts;   // pax_plan_set_column_share
-    // the queued launch (k_ax_fan_queued): blocks of 16 columns in the same order, and one counter per SM
+    // the queued launch (k_ax_fan_queued): blocks of 16 columns in the same order, and the counter the warps take from
     std::vector<int> h_fan_order_q;
     int *d_fan_order_q;             // inside d_fan_order's allocation
-    int *d_fan_queue;               // PAX_FAN_MAXQ counters, cleared before every queued launch
+    int *d_fan_queue;               // the counter (PAX_FAN_MAXQ ints reserved), cleared before every queued launch
     int fan_bw;                     // columns per block
     int fan_queued;                 // 1: launches that own all columns and are not split go through the queues
 };
-#define PAX_FAN_MAXQ 256
+#define PAX_FAN_MAXQ 4
 
 
 // arguments shared by the two forward-projector kernels (ax.cu ray march, ax_fan.cu fan planes)
@@ -91,9 +91,10 @@ struct AxArgs {
     int fan_split;                // ax_fan.cu: parts the launch is cut into along the chords (1: none)
     float *fan_scratch;           // ax_fan.cu: [fan_split][count][V][U] raw sums of a split launch
     int accumulate;               // ax_fan.cu, PLAIN: out += instead of out = (second channel pass)
-    int *fan_queue;               // ax_fan.cu, queued launch: next column of every SM's queue
+    int *fan_queue;               // ax_fan.cu, queued launch: next column of the launch
     int fan_bw;                   // ax_fan.cu, queued launch: columns per block
-    int fan_nqueue, fan_nblock;   // ax_fan.cu, queued launch: queues (SMs) and blocks of columns in the launch
+    int fan_nblock;               // ax_fan.cu, queued launch: blocks of columns in the launch
+    int fan_sms;                  // ax_fan.cu, queued launch: SMs of the device (the grid is fan_minb CTAs on each)
     int fan_nband;                // ax_fan.cu, queued launch: row bands (grid.y of the plain launch)
     int *fault;                   // ax_fan.cu: set to 1 if a single row's z range did not fit the lanes (never, by construction)
 };
