@@ -1,6 +1,6 @@
 """Ax + residual of a few angles of C2 (what a rank of a multi-GPU run launches per subset), best of 12.
 
-    PAX_FAN_QUEUED=0|1|2 PAX_FAN_NQ=n python tools/time_small_launch.py
+    PAX_FAN_QUEUED=0|1|2 python tools/time_small_launch.py      (0: grid launch, 1: queue for unsplit launches, 2: for all)
 """
 import os
 import sys
