@@ -462,13 +462,34 @@ def _v_variant_b(geo, angles, blocks):
     return out
 
 
+# W / V definitions ossart() uses when the caller names none (the reference's TIGRE checkout is
+# un-pinned and the definitions changed between builds).  'matlab' / 'A' -- current upstream's, and the pair a
+# half-fan scan needs -- unless set_default_variants() chose otherwise: compat.install() selects the mid-2021
+# Python package's ('python2021' / 'B'), the build the reference script was written against.
+_DEFAULT_VARIANTS = {"w_variant": "matlab", "v_variant": "A"}
+
+
+def set_default_variants(w_variant=None, v_variant=None):
+    """Choose the W / V definitions of ossart() calls that do not name them; returns the previous pair."""
+    prev = (_DEFAULT_VARIANTS["w_variant"], _DEFAULT_VARIANTS["v_variant"])
+    if w_variant is not None:
+        if w_variant not in ("matlab", "python2021"):
+            raise ValueError(f"unknown W variant {w_variant!r}")
+        _DEFAULT_VARIANTS["w_variant"] = w_variant
+    if v_variant is not None:
+        if v_variant not in ("A", "B"):
+            raise ValueError(f"unknown V variant {v_variant!r}")
+        _DEFAULT_VARIANTS["v_variant"] = v_variant
+    return prev
+
+
 def ossart(proj, geo, angles, niter, **kwargs):
     """OS-SART with TIGRE's signature and defaults (A.6).
 
     kwargs: blocksize=20, lmbda=1, lmbda_red=0.99, OrderStrategy=None, init=None,
     noneg=True, verbose=False, computel2=False, Quameasopts=None (a subset of RMSE / CC / MSSIM / UQI, measured
     between the iterate before and after every iteration: utilities/quality.py), gpuids=None; build extras: w_variant,
-    v_variant, group / distributed / shard (sharding over a torch.distributed group; dist.py),
+    v_variant (default: set_default_variants), group / distributed / shard (sharding over a torch.distributed group; dist.py),
     fused_update (the multi-GPU update as one kernel over symmetric memory; include/pax.h).
     Returns the (Z,Y,X) float32 volume (NumPy in -> NumPy out); with computel2 also the
     per-iteration ||b - Ax||_2.
@@ -488,6 +509,9 @@ def ossart(proj, geo, angles, niter, **kwargs):
         quameas = check_opts(quameas)
     state_kw = {k: kwargs.pop(k) for k in ("w_variant", "v_variant", "group", "distributed", "shard",
                                            "fused_update") if k in kwargs}
+    for k, v in _DEFAULT_VARIANTS.items():
+        if state_kw.get(k) is None:
+            state_kw[k] = v
     if kwargs:
         raise TypeError(f"ossart: unexpected keyword arguments {sorted(kwargs)}")
     if not torch.cuda.is_available():
@@ -513,8 +537,8 @@ def ossart(proj, geo, angles, niter, **kwargs):
         from ..multidev import MultiDevice
         md = MultiDevice(geo, angles, devs, blocksize=blocksize, OrderStrategy=order)
         x0 = None if init is None else _to_cuda(init, md.devices[0], "init")[0]
-        res = md.ossart(proj, niter, lmbda, lmbda_red, noneg, x0, state_kw.get("w_variant", "matlab"),
-                        state_kw.get("v_variant", "A"), computel2, verbose)
+        res = md.ossart(proj, niter, lmbda, lmbda_red, noneg, x0, state_kw["w_variant"],
+                        state_kw["v_variant"], computel2, verbose)
         was_np = isinstance(proj, np.ndarray)
         if computel2:
             return (res[0].cpu().numpy() if was_np else res[0]), res[1]

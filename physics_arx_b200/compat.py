@@ -65,10 +65,19 @@ def _sitk_module():
     return m
 
 
-def install(simpleitk="auto"):
+def install(simpleitk="auto", tigre_build="2021"):
     """Register this package as ``tigre`` (+ submodules).  ``simpleitk``: 'auto' registers the io_nrrd-backed
     ``SimpleITK`` shim when the real package is not importable (it is not in this image), True always, False
-    never -- so that the reference script (which does ``import SimpleITK as sitk``, :15) runs unmodified."""
+    never -- so that the reference script (which does ``import SimpleITK as sitk``, :15) runs unmodified.
+    ``tigre_build``: whose W / V weights ``algorithms.ossart`` applies when the caller names none (the script
+    does not, :101-103) -- '2021': the Python package of mid-2021 the script was written against (W from the
+    DSD-DSO cube with threshold min(dVoxel)/4, analytic V), 'upstream': current TIGRE's (MATLAB
+    ``computeW``, V = Atb(ones): what a half-fan scan needs), None: leave the package's setting alone."""
+    if tigre_build is not None:
+        if tigre_build not in ("2021", "upstream"):
+            raise ValueError(f"tigre_build must be '2021', 'upstream' or None, got {tigre_build!r}")
+        from .algorithms.ossart import set_default_variants
+        set_default_variants(*(("python2021", "B") if tigre_build == "2021" else ("matlab", "A")))
     me = sys.modules[__name__]
     sys.modules.setdefault("tigre", me)
     sys.modules.setdefault("tigre.algorithms", algorithms)

@@ -51,11 +51,12 @@ def list_cases(in_dir):
 
 def pCT_CBCT_reconstruction(in_dir, niter=30, blocksize=20, n_angles=500, Poisson=1e8,
                             Gaussian=np.array([0, 4]), seed=0, half_fan=False, save_projections=True,
-                            verbose=True, w_variant="matlab", v_variant="A"):
+                            verbose=True, w_variant=None, v_variant=None):
     """The reference script's loop (module docstring).  ``w_variant`` / ``v_variant`` choose between the W / V
-    definitions of TIGRE's builds (the script's TIGRE checkout is un-pinned): the defaults are
-    current upstream's (MATLAB ``computeW``; V from ``Atb(ones)``, the variant half-fan needs), ``'python2021'``
-    / ``'B'`` are those of the mid-2021 Python package the script's date points at."""
+    definitions of TIGRE's builds (the script's TIGRE checkout is un-pinned).  Default: those of
+    the mid-2021 Python package the script was written against (``'python2021'`` / ``'B'``), as
+    ``compat.install()`` gives the script itself; with ``half_fan`` current upstream's (``'matlab'`` / ``'A'``:
+    MATLAB ``computeW``, V from ``Atb(ones)``), which an offset detector needs."""
     import torch
 
     from . import Ax
@@ -63,6 +64,10 @@ def pCT_CBCT_reconstruction(in_dir, niter=30, blocksize=20, n_angles=500, Poisso
     from .io_nrrd import read_nrrd, write_nrrd
     from .utilities import CTnoise, gpu
 
+    if w_variant is None:
+        w_variant = "matlab" if half_fan else "python2021"
+    if v_variant is None:
+        v_variant = "A" if half_fan else "B"
     names = gpu.getGpuNames()
     if len(names) == 0:
         raise RuntimeError("Error: No gpu found")          # the reference prints this and then fails (:25-31)

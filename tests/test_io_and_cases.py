@@ -85,7 +85,8 @@ def test_case_driver_end_to_end(tmp_path, oracle):
     npz = np.load(os.path.join(str(tmp_path), "P1", "Artifacts", "P1_projections_0.5_0.5.npz"))
     assert npz["projection"].shape == (30, 400, 400)
     geo, angles = case_geometry((20, 20, 20), (8.0, 8.0, 8.0)), np.linspace(0, 2 * np.pi, 30)
-    ref = oracle.ossart(npz["projection"], geo, angles, 2, blocksize=10)
+    # the driver's defaults are the W / V of the TIGRE build the script was written against (A.5)
+    ref = oracle.ossart(npz["projection"], geo, angles, 2, blocksize=10, w_variant="python2021", v_variant="B")
     hu = np.abs(out.array - ref) * 4095.0
     assert hu.mean() <= 1.0 and hu.max() <= 5.0
 
@@ -103,8 +104,16 @@ def test_simpleitk_shim_round_trip(tmp_path):
     from physics_arx_b200 import compat
     saved = {k: sys.modules.get(k) for k in ("tigre", "tigre.algorithms", "tigre.utilities",
                                              "tigre.utilities.CTnoise", "tigre.utilities.gpu", "SimpleITK")}
+    from physics_arx_b200.algorithms.ossart import _DEFAULT_VARIANTS, set_default_variants
+    before = set_default_variants()
     try:
         compat.install(simpleitk=True)
+        # the script names no W / V variant: install() selects the mid-2021 Python package's
+        assert _DEFAULT_VARIANTS == {"w_variant": "python2021", "v_variant": "B"}
+        compat.install(simpleitk=True, tigre_build="upstream")
+        assert _DEFAULT_VARIANTS == {"w_variant": "matlab", "v_variant": "A"}
+        with pytest.raises(ValueError):
+            compat.install(tigre_build="3.0")
         import SimpleITK as sitk
         vol = _make_patient(str(tmp_path))
         src = os.path.join(str(tmp_path), "P1", "Artifacts", "P1_pCT_Artifact_1_0_rsc.nrrd")
@@ -119,6 +128,7 @@ def test_simpleitk_shim_round_trip(tmp_path):
         import tigre
         assert tigre.Ax is compat.Ax
     finally:
+        set_default_variants(*before)
         for k, v in saved.items():
             if v is None:
                 sys.modules.pop(k, None)
@@ -146,12 +156,15 @@ def test_unmodified_reference_script_runs_on_this_package(tmp_path):
     saved = {k: sys.modules.get(k) for k in ("tigre", "tigre.algorithms", "tigre.utilities",
                                              "tigre.utilities.CTnoise", "tigre.utilities.gpu", "SimpleITK")}
     cwd = os.getcwd()
+    from physics_arx_b200.algorithms.ossart import set_default_variants
+    before = set_default_variants()
     try:
         compat.install()
         os.chdir(str(work))
         runpy.run_path(REF_SCRIPT, run_name="reference_script")
     finally:
         os.chdir(cwd)
+        set_default_variants(*before)
         for k, v in saved.items():
             if v is None:
                 sys.modules.pop(k, None)
