@@ -31,6 +31,8 @@
 // accumulates and 2 STS.128 of its running (A, C) into a ring of CW steps.  After every CW steps the lanes
 // enumerate the rows that crossed their boundaries (closed form: a row interval per boundary), and the warp
 // serves those events 32 at a time from the ring; at the end of an epoch every row reads its pair once.
+// The warps are independent (no CTA barrier); by default they are persistent and take their columns from a
+// counter (k_ax_fan_queued), the plain grid launch (k_ax_fan) serves column shares and chord-split launches.
 #include <algorithm>
 #include <climits>
 #include <cmath>
