@@ -93,7 +93,10 @@ class SCBCTPipeline:
         with torch.cuda.device(self.device):
             pos = 0
             if self.n_local:
-                for g0, cnt in _contiguous_runs(self.local_idx):      # runs of consecutive global angles
+                # one launch per run of consecutive global angles: one in all on a single GPU, one per subset in the
+                # default multi-GPU scheme (a rank owns a contiguous share of every subset's angles), one per angle
+                # with the interleaved shares of PAX_MGPU=reduce (656 / N launches of ~10 us, once per volume)
+                for g0, cnt in _contiguous_runs(self.local_idx):
                     view = st.b[pos:pos + cnt]
                     _lib.check(lib.pax_ctnoise(_ptr(view), view.numel(),
                                                ctypes.c_uint64(int(g0) * npix + first), inner,
